@@ -1,0 +1,150 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention library
+ * (libmsda_b200.so, hand-written sm_100a CUDA, no ATen / pybind / torch types).
+ *
+ * This is the drop-in boundary for the hot path of JimmyZou/Snipper.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference repo):
+ *
+ *   msda_forward            <- ms_deform_attn_forward / ms_deform_attn_cuda_forward
+ *                              models/ops/src/ms_deform_attn.h:20-39,
+ *                              models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80,
+ *                              launcher ms_deformable_im2col_cuda  ms_deform_im2col_cuda.cuh:923-954
+ *   msda_backward           <- ms_deform_attn_backward / ms_deform_attn_cuda_backward
+ *                              models/ops/src/ms_deform_attn.h:41-61,
+ *                              models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153,
+ *                              launcher ms_deformable_col2im_cuda  ms_deform_im2col_cuda.cuh:956-1327
+ *   msda_snippet_forward /  <- the per-frame loop of MSDeformAttn.forward
+ *   msda_snippet_backward      models/ops/modules/ms_deform_attn.py:126-225 (offset normalisation,
+ *                              softmax over levels x points x neighbour frames, one op call per
+ *                              (t1,t2) pair, sum over t2) fused into one launch per layer
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer; the caller owns every buffer; the library allocates
+ *     nothing, never synchronises and only enqueues work on `stream` (a cudaStream_t).
+ *   - spatial_shapes (L,2) = (H_l, W_l) and level_start_index (L) are int64 ON THE DEVICE
+ *     (the reference builds them there, models/deformable_transformer.py:100-101); they are
+ *     read inside the kernels -- no host sync.
+ *   - layouts as in the reference: value (N,S,M,D); sampling_loc (N,Lq,M,L,P,2) as (x,y) in
+ *     [0,1] incl. padding; attn_weight (N,Lq,M,L,P); output (N,Lq,M*D).
+ *   - every function returns an msda_status_t (0 = ok).  Launch failures are returned, not
+ *     printed (the reference only printf()s them, ms_deform_im2col_cuda.cuh:948-952).
+ *   - re-entrant and stateless.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MSDA_API __attribute__((visibility("default")))
+#else
+#define MSDA_API
+#endif
+
+typedef enum {
+    MSDA_OK = 0,
+    MSDA_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive size, bad stride/alignment   */
+    MSDA_ERR_IM2COL_STEP = 2,      /* batch % min(batch, im2col_step) != 0 (cu:50-52)        */
+    MSDA_ERR_UNSUPPORTED_DTYPE = 3,
+    MSDA_ERR_WORKSPACE = 4,        /* deterministic mode: workspace missing or too small     */
+    MSDA_ERR_TOO_LARGE = 5,        /* a 32-bit in-kernel index would overflow                */
+    MSDA_ERR_CUDA = 6              /* cudaGetLastError() != cudaSuccess after a launch       */
+} msda_status_t;
+
+typedef enum {
+    MSDA_DTYPE_F32 = 0,
+    MSDA_DTYPE_F64 = 1,
+    MSDA_DTYPE_BF16 = 2 /* value/output/grad_output in bf16, fp32 accumulate; loc/attn stay fp32 */
+} msda_dtype_t;
+
+/* msda_backward / msda_snippet_backward flags */
+#define MSDA_FLAG_DETERMINISTIC 1u   /* two-pass, atomics-free grad_value (needs workspace)   */
+#define MSDA_FLAG_ACCUMULATE_VALUE 2u /* add into grad_value instead of zero-filling it first */
+
+MSDA_API int msda_abi_version(void);
+MSDA_API const char *msda_error_string(int status);
+/* cudaError_t of the last failed launch seen by this thread (0 if none). */
+MSDA_API int msda_last_cuda_error(void);
+
+/*
+ * Forward.  output[n,q,m*D+c] = sum_{l,p} attn[n,q,m,l,p] * bilinear(value_l[n,:,m,c], loc[n,q,m,l,p])
+ * value_batch_stride: elements between consecutive batch items of `value`
+ *                     (0 means S*M*D, i.e. contiguous) -- lets a caller pass value[:, t2]
+ *                     without the copy the reference makes (ms_deform_attn.py:179).
+ * im2col_step: validated like the reference (MSDA_ERR_IM2COL_STEP); the whole batch is then
+ *              processed by one launch -- results do not depend on the chunking.
+ */
+MSDA_API int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, int64_t value_batch_stride, int im2col_step,
+                 int dtype, void *stream);
+
+/*
+ * Backward.  Writes grad_sampling_loc (N,Lq,M,L,P,2) and grad_attn_weight (N,Lq,M,L,P) in full;
+ * grad_value (N,S,M,D, contiguous) is zero-filled first unless MSDA_FLAG_ACCUMULATE_VALUE.
+ * With MSDA_FLAG_DETERMINISTIC the result is bit-reproducible run to run; pass a workspace of
+ * at least msda_backward_workspace_bytes(...) bytes (256-byte aligned).
+ */
+MSDA_API int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                  void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                  int num_query, int num_point, int64_t value_batch_stride, int im2col_step,
+                  int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream);
+
+MSDA_API size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                     int num_levels, int num_query, int num_point, int dtype,
+                                     unsigned flags);
+
+/*
+ * Fused Snipper snippet attention (one launch per transformer layer).
+ *   value            (N,T2,S,M,D)       element strides value_stride_n / value_stride_t
+ *   offsets          (N,T1,Lq,M,L,P,2)  raw sampling_offsets Linear output, in pixels, contiguous
+ *   logits           (N,T1,Lq,M,L,P)    raw attention_weights Linear output, contiguous
+ *   reference_points (N,T1,Lq,L,2)      element strides ref_stride_n / ref_stride_t (0 allowed:
+ *                                       the encoder expands one frame over T1)
+ *   output           (N,T1,Lq,M*D)      contiguous
+ * Per (n,t1,q,m): A = softmax_{l,p}(logits) / k,  loc = ref + offsets / (W_l,H_l),
+ * out = sum over the k neighbour frames t2 of msda(value[:,t2], loc, A); neighbour frames are
+ * {t1-1,t1,t1+1} clipped to [0,n_frame) for t1 < n_frame, all T2 frames otherwise
+ * (ms_deform_attn.py:137-140,189,201).  Requires the frame slots to share one Linear
+ * (ms_deform_attn.py:68-71), which makes logits/offsets identical across t2.
+ * float32 only; L*P <= 32; D % 16 == 0; D <= 128.
+ */
+MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
+                         const int64_t *level_start_index, const void *offsets, const void *logits,
+                         const void *reference_points, void *output,
+                         int batch, int n_src_frames, int n_query_frames, int n_frame,
+                         int spatial_size, int num_heads, int channels, int num_levels,
+                         int num_query, int num_point,
+                         int64_t value_stride_n, int64_t value_stride_t,
+                         int64_t ref_stride_n, int64_t ref_stride_t, int dtype, void *stream);
+
+/*
+ * grad_value (N,T2,S,M,D contiguous; zero-filled unless MSDA_FLAG_ACCUMULATE_VALUE),
+ * grad_offsets like offsets, grad_logits like logits.  The gradient w.r.t. reference_points
+ * is sum_{m,p} grad_offsets * (W_l,H_l) and is left to the caller.
+ */
+MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start_index, const void *offsets, const void *logits,
+                          const void *reference_points, const void *grad_output,
+                          void *grad_value, void *grad_offsets, void *grad_logits,
+                          int batch, int n_src_frames, int n_query_frames, int n_frame,
+                          int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point,
+                          int64_t value_stride_n, int64_t value_stride_t,
+                          int64_t ref_stride_n, int64_t ref_stride_t, int dtype, unsigned flags,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

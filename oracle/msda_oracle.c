@@ -19,17 +19,21 @@
 #define REAL double
 #define SUFFIX f64
 #define FLOOR floor
+#define FMA fma
 #include "msda_oracle_body.inc"
 #undef REAL
 #undef SUFFIX
 #undef FLOOR
+#undef FMA
 
 #define REAL float
 #define SUFFIX f32
 #define FLOOR floorf
+#define FMA fmaf
 #include "msda_oracle_body.inc"
 #undef REAL
 #undef SUFFIX
 #undef FLOOR
+#undef FMA
 
 int msda_oracle_abi_version(void) { return 1; }

@@ -1,0 +1,252 @@
+// extern "C" entry points of libmsda_b200.so (see include/msda_b200.h for the contract and
+// the reference interfaces each one replaces).  Argument validation mirrors the reference host
+// code (models/ops/src/cuda/ms_deform_attn_cuda.cu:28-52) but reports through return codes.
+#include "../../include/msda_b200.h"
+#include "msda_internal.h"
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+
+int cuda_status(cudaError_t e)
+{
+    if (e == cudaSuccess) return MSDA_OK;
+    g_last_cuda_error = (int)e;
+    return MSDA_ERR_CUDA;
+}
+
+int check_common(const void *const *ptrs, int nptrs, int batch, int spatial_size, int num_heads,
+                 int channels, int num_levels, int num_query, int num_point)
+{
+    if (batch < 0 || spatial_size < 0 || num_query < 0) return MSDA_ERR_INVALID_ARGUMENT;
+    if (num_heads <= 0 || channels <= 0 || num_levels <= 0 || num_point <= 0) return MSDA_ERR_INVALID_ARGUMENT;
+    if (num_levels > msda::kMaxLevels) return MSDA_ERR_INVALID_ARGUMENT;
+    const bool empty = (batch == 0 || num_query == 0);
+    if (!empty)
+        for (int i = 0; i < nptrs; ++i)
+            if (ptrs[i] == nullptr) return MSDA_ERR_INVALID_ARGUMENT;
+    return MSDA_OK;
+}
+
+// reference ms_deform_attn_cuda.cu:50-52
+int check_im2col_step(int batch, int im2col_step)
+{
+    if (batch == 0) return MSDA_OK;
+    if (im2col_step <= 0) return MSDA_ERR_IM2COL_STEP;
+    const int step = batch < im2col_step ? batch : im2col_step;
+    return (batch % step == 0) ? MSDA_OK : MSDA_ERR_IM2COL_STEP;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+int msda_last_cuda_error(void) { return g_last_cuda_error; }
+
+const char *msda_error_string(int status)
+{
+    switch (status) {
+        case MSDA_OK: return "ok";
+        case MSDA_ERR_INVALID_ARGUMENT: return "invalid argument (null pointer, bad size, stride or alignment)";
+        case MSDA_ERR_IM2COL_STEP: return "batch must divide im2col_step";
+        case MSDA_ERR_UNSUPPORTED_DTYPE: return "unsupported dtype for this entry point";
+        case MSDA_ERR_WORKSPACE: return "deterministic mode needs a workspace of msda_backward_workspace_bytes()";
+        case MSDA_ERR_TOO_LARGE: return "problem too large for 32-bit in-kernel indices";
+        case MSDA_ERR_CUDA: return "CUDA launch failed (see msda_last_cuda_error)";
+        default: return "unknown msda status";
+    }
+}
+
+int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, int64_t value_batch_stride, int im2col_step,
+                 int dtype, void *stream)
+{
+    const void *ptrs[] = {value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output};
+    int st = check_common(ptrs, 6, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+    if (st != MSDA_OK) return st;
+    st = check_im2col_step(batch, im2col_step);
+    if (st != MSDA_OK) return st;
+    if (batch == 0 || num_query == 0) return MSDA_OK;
+    if (value_batch_stride == 0) value_batch_stride = (int64_t)spatial_size * num_heads * channels;
+    if (value_batch_stride < 0) return MSDA_ERR_INVALID_ARGUMENT;
+    msda::OpDims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, value_batch_stride};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (spatial_size == 0) {  // nothing to sample: every corner is invalid
+        const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : 4;
+        if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64) return MSDA_ERR_UNSUPPORTED_DTYPE;
+        return cuda_status(cudaMemsetAsync(output, 0, esz * batch * num_query * num_heads * channels, s));
+    }
+    switch (dtype) {
+        case MSDA_DTYPE_F32:
+            if (msda::fast_path_ok(d) && aligned16(value) && aligned16(output))
+                return cuda_status(msda::launch_forward_fast_f32(
+                    (const float *)value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+                    (const float *)attn_weight, (float *)output, d, s));
+            return cuda_status(msda::launch_forward_generic<float>(
+                (const float *)value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+                (const float *)attn_weight, (float *)output, d, s));
+        case MSDA_DTYPE_F64:
+            return cuda_status(msda::launch_forward_generic<double>(
+                (const double *)value, spatial_shapes, level_start_index, (const double *)sampling_loc,
+                (const double *)attn_weight, (double *)output, d, s));
+        default:
+            return MSDA_ERR_UNSUPPORTED_DTYPE;
+    }
+}
+
+size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                     int num_levels, int num_query, int num_point, int dtype,
+                                     unsigned flags)
+{
+    if (!(flags & MSDA_FLAG_DETERMINISTIC) || dtype != MSDA_DTYPE_F32) return 0;
+    msda::OpDims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, 0};
+    return msda::deterministic_workspace_bytes(d);
+}
+
+int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                  void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                  int num_query, int num_point, int64_t value_batch_stride, int im2col_step,
+                  int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream)
+{
+    const void *ptrs[] = {value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                          grad_output, grad_value, grad_sampling_loc, grad_attn_weight};
+    int st = check_common(ptrs, 9, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+    if (st != MSDA_OK) return st;
+    st = check_im2col_step(batch, im2col_step);
+    if (st != MSDA_OK) return st;
+    if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (value_batch_stride == 0) value_batch_stride = (int64_t)spatial_size * num_heads * channels;
+    if (value_batch_stride < 0) return MSDA_ERR_INVALID_ARGUMENT;
+    msda::OpDims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, value_batch_stride};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : 4;
+    const size_t value_elems = (size_t)batch * spatial_size * num_heads * channels;
+    if (!(flags & MSDA_FLAG_ACCUMULATE_VALUE) && value_elems > 0 && grad_value != nullptr) {
+        st = cuda_status(cudaMemsetAsync(grad_value, 0, esz * value_elems, s));
+        if (st != MSDA_OK) return st;
+    }
+    if (batch == 0 || num_query == 0) return MSDA_OK;
+    if (spatial_size == 0) {
+        const size_t n = (size_t)batch * num_query * num_heads * num_levels * num_point;
+        st = cuda_status(cudaMemsetAsync(grad_sampling_loc, 0, esz * 2 * n, s));
+        if (st != MSDA_OK) return st;
+        return cuda_status(cudaMemsetAsync(grad_attn_weight, 0, esz * n, s));
+    }
+    if (dtype == MSDA_DTYPE_F64) {
+        if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_UNSUPPORTED_DTYPE;
+        return cuda_status(msda::launch_backward_generic<double>(
+            (const double *)value, spatial_shapes, level_start_index, (const double *)sampling_loc,
+            (const double *)attn_weight, (const double *)grad_output, (double *)grad_value,
+            (double *)grad_sampling_loc, (double *)grad_attn_weight, d, s));
+    }
+    if (flags & MSDA_FLAG_DETERMINISTIC) {
+        const size_t need = msda::deterministic_workspace_bytes(d);
+        if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+            return MSDA_ERR_WORKSPACE;
+        return cuda_status(msda::launch_backward_deterministic_f32(
+            (const float *)value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+            (const float *)attn_weight, (const float *)grad_output, (float *)grad_value,
+            (float *)grad_sampling_loc, (float *)grad_attn_weight, d, workspace, s));
+    }
+    if (msda::fast_path_ok(d) && aligned16(value) && aligned16(grad_output) && aligned16(grad_value))
+        return cuda_status(msda::launch_backward_fast_f32(
+            (const float *)value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+            (const float *)attn_weight, (const float *)grad_output, (float *)grad_value,
+            (float *)grad_sampling_loc, (float *)grad_attn_weight, d, s));
+    return cuda_status(msda::launch_backward_generic<float>(
+        (const float *)value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+        (const float *)attn_weight, (const float *)grad_output, (float *)grad_value,
+        (float *)grad_sampling_loc, (float *)grad_attn_weight, d, s));
+}
+
+static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n_query_frames,
+                        int n_frame, int spatial_size, int num_heads, int channels, int num_levels,
+                        int num_query, int num_point, int64_t value_stride_n, int64_t value_stride_t,
+                        int64_t ref_stride_n, int64_t ref_stride_t, int dtype)
+{
+    if (dtype != MSDA_DTYPE_F32) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (batch < 0 || num_query < 0 || n_src_frames <= 0 || n_query_frames <= 0 || n_frame <= 0 ||
+        n_frame > n_src_frames || spatial_size <= 0 || num_heads <= 0 || channels <= 0 ||
+        num_levels <= 0 || num_point <= 0)
+        return MSDA_ERR_INVALID_ARGUMENT;
+    if (value_stride_t == 0) value_stride_t = (int64_t)spatial_size * num_heads * channels;
+    if (value_stride_n == 0) value_stride_n = value_stride_t * n_src_frames;
+    if (value_stride_n < 0 || value_stride_t < 0 || ref_stride_n < 0 || ref_stride_t < 0)
+        return MSDA_ERR_INVALID_ARGUMENT;
+    d = msda::SnippetDims{batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
+                          channels, num_levels, num_query, num_point, value_stride_n,
+                          value_stride_t, ref_stride_n, ref_stride_t};
+    if (!msda::snippet_ok(d)) return MSDA_ERR_INVALID_ARGUMENT;
+    return MSDA_OK;
+}
+
+int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
+                         const int64_t *level_start_index, const void *offsets, const void *logits,
+                         const void *reference_points, void *output,
+                         int batch, int n_src_frames, int n_query_frames, int n_frame,
+                         int spatial_size, int num_heads, int channels, int num_levels,
+                         int num_query, int num_point,
+                         int64_t value_stride_n, int64_t value_stride_t,
+                         int64_t ref_stride_n, int64_t ref_stride_t, int dtype, void *stream)
+{
+    msda::SnippetDims d;
+    int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
+                          channels, num_levels, num_query, num_point, value_stride_n,
+                          value_stride_t, ref_stride_n, ref_stride_t, dtype);
+    if (st != MSDA_OK) return st;
+    if (batch == 0 || num_query == 0) return MSDA_OK;
+    if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points || !output)
+        return MSDA_ERR_INVALID_ARGUMENT;
+    if (!aligned16(value) || !aligned16(output) || !aligned16(offsets) || !aligned16(logits))
+        return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_snippet_forward_f32(
+        (const float *)value, spatial_shapes, level_start_index, (const float *)offsets,
+        (const float *)logits, (const float *)reference_points, (float *)output, d,
+        static_cast<cudaStream_t>(stream)));
+}
+
+int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start_index, const void *offsets, const void *logits,
+                          const void *reference_points, const void *grad_output,
+                          void *grad_value, void *grad_offsets, void *grad_logits,
+                          int batch, int n_src_frames, int n_query_frames, int n_frame,
+                          int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point,
+                          int64_t value_stride_n, int64_t value_stride_t,
+                          int64_t ref_stride_n, int64_t ref_stride_t, int dtype, unsigned flags,
+                          void *stream)
+{
+    msda::SnippetDims d;
+    int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
+                          channels, num_levels, num_query, num_point, value_stride_n,
+                          value_stride_t, ref_stride_n, ref_stride_t, dtype);
+    if (st != MSDA_OK) return st;
+    if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t value_elems = (size_t)batch * n_src_frames * spatial_size * num_heads * channels;
+    if (!(flags & MSDA_FLAG_ACCUMULATE_VALUE) && value_elems > 0) {
+        if (!grad_value) return MSDA_ERR_INVALID_ARGUMENT;
+        st = cuda_status(cudaMemsetAsync(grad_value, 0, sizeof(float) * value_elems, s));
+        if (st != MSDA_OK) return st;
+    }
+    if (batch == 0 || num_query == 0) return MSDA_OK;
+    if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points ||
+        !grad_output || !grad_value || !grad_offsets || !grad_logits)
+        return MSDA_ERR_INVALID_ARGUMENT;
+    if (!aligned16(value) || !aligned16(grad_output) || !aligned16(grad_value))
+        return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_snippet_backward_f32(
+        (const float *)value, spatial_shapes, level_start_index, (const float *)offsets,
+        (const float *)logits, (const float *)reference_points, (const float *)grad_output,
+        (float *)grad_value, (float *)grad_offsets, (float *)grad_logits, d, s));
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Device helpers shared by the per-call and the fused snippet kernels (sm_100a).
+//
+// Data layout in HBM (all row-major, as the reference op):
+//   value   (N, S, M, D)          one "cell" = the D channels of head m at flattened pixel s
+//   loc     (N, Lq, M, L, P, 2)   (x, y) normalised;  attn (N, Lq, M, L, P)
+//   out     (N, Lq, M, D)
+// A "pair" is one (n, q, m); it owns L*P "samples" (one per level x point); a sample touches
+// up to four cells.  Math follows reference ms_deform_im2col_cuda.cuh:33-84 (forward),
+// :87-159 (backward), :272-296 (pixel convention / range test).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_internal.h"
+
+namespace msda {
+
+// Level table staged once per CTA in shared memory (the int64 device tensors are never
+// re-read per level/point as the reference does, ms_deform_im2col_cuda.cuh:272-281).
+struct LevelTable {
+    int H[kMaxLevels];
+    int W[kMaxLevels];
+    int start[kMaxLevels];
+};
+
+__device__ __forceinline__ void load_level_table(LevelTable &t, const int64_t *__restrict__ shapes,
+                                                 const int64_t *__restrict__ lsi, int L)
+{
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        t.H[l] = (int)shapes[2 * l];
+        t.W[l] = (int)shapes[2 * l + 1];
+        t.start[l] = (int)lsi[l];
+    }
+}
+
+// One bilinear sample: fractional parts and the four cell indices (start + y*W + x) or -1
+// for a corner that falls outside the level / a sample outside (-1,W)x(-1,H).
+template <typename real>
+struct Sample {
+    int cell[4];
+    real lx, ly;
+};
+
+template <typename real>
+__device__ __forceinline__ Sample<real> make_sample(real u, real v, int H, int W, int start)
+{
+    Sample<real> s;
+    // explicit single-rounding FMA (what nvcc makes of the reference's `loc_w * spatial_w - 0.5`,
+    // ms_deform_im2col_cuda.cuh:285-286); the CPU oracle does the same, so floor() agrees bit for bit
+    const real x = fma(u, (real)W, (real)-0.5);
+    const real y = fma(v, (real)H, (real)-0.5);
+    const bool active = (x > (real)-1) && (y > (real)-1) && (x < (real)W) && (y < (real)H);
+    const real fx = floor(x), fy = floor(y);
+    s.lx = x - fx;
+    s.ly = y - fy;
+    const int x0 = active ? (int)fx : 0, y0 = active ? (int)fy : 0;
+    const bool vx0 = active && x0 >= 0, vx1 = active && x0 + 1 <= W - 1;
+    const bool vy0 = y0 >= 0, vy1 = y0 + 1 <= H - 1;
+    const int base = start + y0 * W + x0;
+    s.cell[0] = (vy0 && vx0) ? base : -1;
+    s.cell[1] = (vy0 && vx1) ? base + 1 : -1;
+    s.cell[2] = (vy1 && vx0) ? base + W : -1;
+    s.cell[3] = (vy1 && vx1) ? base + W + 1 : -1;
+    if (!active) { s.lx = (real)0; s.ly = (real)0; }
+    return s;
+}
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// 128-bit vector reduction to global memory (sm_90+): one L2 atomic op per 16 bytes
+// instead of four scalar REDs (the reference issues scalar atomicAdd per channel,
+// ms_deform_im2col_cuda.cuh:125-152).
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :
+                 : "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b)
+{
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+}  // namespace msda

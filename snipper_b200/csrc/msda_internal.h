@@ -1,0 +1,66 @@
+// Internal launcher interface between the C ABI (msda_capi.cu) and the kernel files.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace msda {
+
+constexpr int kMaxLevels = 64;
+
+struct OpDims {
+    int N, S, M, D, L, Lq, P;
+    int64_t value_batch_stride;  // elements
+};
+
+struct SnippetDims {
+    int N, T2, T1, n_frame, S, M, D, L, Lq, P;
+    int64_t value_stride_n, value_stride_t;  // elements
+    int64_t ref_stride_n, ref_stride_t;      // elements
+};
+
+// ---- per-call op (msda_percall.cu) ----
+// fast = vectorised fp32 path (D % 16 == 0, D <= 256); generic = any D, float or double.
+bool fast_path_ok(const OpDims &d);
+
+cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                    const float *loc, const float *attn, float *out,
+                                    const OpDims &d, cudaStream_t stream);
+cudaError_t launch_backward_fast_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                     const float *loc, const float *attn, const float *grad_out,
+                                     float *grad_value, float *grad_loc, float *grad_attn,
+                                     const OpDims &d, cudaStream_t stream);
+
+template <typename T>
+cudaError_t launch_forward_generic(const T *value, const int64_t *shapes, const int64_t *lsi,
+                                   const T *loc, const T *attn, T *out, const OpDims &d,
+                                   cudaStream_t stream);
+template <typename T>
+cudaError_t launch_backward_generic(const T *value, const int64_t *shapes, const int64_t *lsi,
+                                    const T *loc, const T *attn, const T *grad_out,
+                                    T *grad_value, T *grad_loc, T *grad_attn, const OpDims &d,
+                                    cudaStream_t stream);
+
+// ---- deterministic backward (msda_deterministic.cu) ----
+size_t deterministic_workspace_bytes(const OpDims &d);
+cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t *shapes,
+                                              const int64_t *lsi, const float *loc,
+                                              const float *attn, const float *grad_out,
+                                              float *grad_value, float *grad_loc, float *grad_attn,
+                                              const OpDims &d, void *workspace, cudaStream_t stream);
+
+// ---- fused snippet op (msda_snippet.cu) ----
+bool snippet_ok(const SnippetDims &d);
+cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes,
+                                       const int64_t *lsi, const float *offsets,
+                                       const float *logits, const float *ref, float *out,
+                                       const SnippetDims &d, cudaStream_t stream);
+cudaError_t launch_snippet_backward_f32(const float *value, const int64_t *shapes,
+                                        const int64_t *lsi, const float *offsets,
+                                        const float *logits, const float *ref,
+                                        const float *grad_out, float *grad_value,
+                                        float *grad_offsets, float *grad_logits,
+                                        const SnippetDims &d, cudaStream_t stream);
+
+}  // namespace msda

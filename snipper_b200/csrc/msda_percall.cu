@@ -1,0 +1,499 @@
+// Per-call multi-scale deformable attention, forward + backward, sm_100a.
+//
+// Replaces the reference launchers ms_deformable_im2col_cuda / ms_deformable_col2im_cuda
+// (models/ops/src/cuda/ms_deform_im2col_cuda.cuh:923-954, :956-1327) and the seven
+// __global__ kernels behind them with two designs:
+//
+//  * FAST (fp32, D % 16 == 0, D <= 128 -- Snipper's D = 48 is the tuned case)
+//      CTA = PAIRS (n,q,m) pairs x LANES (= D/4) lanes, "flat" mapping: consecutive lanes own
+//      consecutive 16-byte channel chunks, so one warp-wide LDG.128 covers whole 192-byte
+//      head slices (2.67 of them) and every gathered cell is read as full 32-byte sectors.
+//      Phase 1: one thread per SAMPLE computes the bilinear set-up once (4 cell offsets +
+//      weights) and parks it in shared memory -- the reference redoes this per channel.
+//      Phase 2: each lane walks the samples of its pair: broadcast LDS of the record,
+//      4 x predicated LDG.128 gathers, FFMA.  Backward additionally issues one
+//      red.global.add.v4.f32 per corner per lane (4x fewer L2 atomics than scalar REDs),
+//      reduces the three per-sample scalars over channels with 2 shuffles inside 4-lane
+//      sub-groups + a tiny smem hop (no serial thread-0 tail, no __syncthreads per point).
+//  * GENERIC (float / double, any D): straightforward one-thread-per-output-element forward
+//      and one-warp-per-pair backward; used for fp64 parity tests and odd channel counts
+//      (the reference's test list 30, 71, 1025, ... models/ops/test.py:85).
+#include "msda_common.cuh"
+#include "msda_internal.h"
+
+namespace msda {
+
+// ------------------------------------------------------------------------------------------
+// FAST fp32 path
+// ------------------------------------------------------------------------------------------
+template <int LANES>
+struct FastCfg {
+    static constexpr int kPairsRaw = (256 / LANES) / 8 * 8;
+    static constexpr int PAIRS = kPairsRaw < 8 ? 8 : kPairsRaw;
+    static constexpr int THREADS = PAIRS * LANES;
+    static constexpr int SUBS = LANES / 4;                              // 4-lane shuffle groups
+    static constexpr int CHUNK = (512 / PAIRS) < 32 ? (512 / PAIRS) : 32;  // samples per pair per pass
+    static_assert(LANES % 4 == 0 && THREADS % 32 == 0, "lane groups must tile warps");
+};
+
+struct __align__(16) FwdRec {
+    int4 off;   // float4-index offsets of the four cells relative to (batch base + m*D), or -1
+    float4 w;   // bilinear weight x attention weight per corner
+};
+
+struct __align__(16) BwdRec {
+    int4 off;
+    float lx, ly, a;
+    int level;
+};
+
+template <int LANES>
+__global__ void __launch_bounds__(FastCfg<LANES>::THREADS)
+msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                     const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                     const float *__restrict__ attn, float *__restrict__ out,
+                     int M, int L, int P, int LqM, int total_pairs, int64_t value_batch_stride,
+                     int cl /* samples per pair per pass */)
+{
+    using Cfg = FastCfg<LANES>;
+    __shared__ LevelTable lv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FwdRec *rec = reinterpret_cast<FwdRec *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int LP = L * P;
+    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const int cell_stride = M * LANES;  // float4 units between consecutive cells
+
+    load_level_table(lv, shapes, lsi, L);
+    __syncthreads();
+
+    const int pl = tid / LANES;
+    const int lane = tid - pl * LANES;
+    const int pair = pair0 + pl;
+    const bool live = pair < total_pairs;
+    const float4 *vbase = nullptr;
+    if (live) {
+        const int b = pair / LqM;
+        const int m = pair % M;
+        vbase = reinterpret_cast<const float4 *>(value + (int64_t)b * value_batch_stride) + m * LANES + lane;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int lp0 = 0; lp0 < LP; lp0 += cl) {
+        const int n = min(cl, LP - lp0);
+        // ---- phase 1: one thread per sample ----
+        for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
+            const int spl = i / n;
+            const int lp = lp0 + (i - spl * n);
+            const int sp = pair0 + spl;
+            FwdRec r;
+            r.off = make_int4(-1, -1, -1, -1);
+            r.w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sp < total_pairs) {
+                const size_t si = (size_t)sp * LP + lp;
+                const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
+                const float a = __ldg(attn + si);
+                const int l = lp / P;
+                const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
+                const float hx = 1.f - s.lx, hy = 1.f - s.ly;
+                r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
+                r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
+                r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
+                r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
+                r.w = make_float4(hy * hx * a, hy * s.lx * a, s.ly * hx * a, s.ly * s.lx * a);
+            }
+            rec[i] = r;
+        }
+        __syncthreads();
+        // ---- phase 2: gather ----
+        if (live) {
+            const FwdRec *my = rec + pl * n;
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                const int4 o = my[j].off;
+                const float4 w = my[j].w;
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+                if (o.x >= 0) v0 = ldg4(vbase + o.x);
+                if (o.y >= 0) v1 = ldg4(vbase + o.y);
+                if (o.z >= 0) v2 = ldg4(vbase + o.z);
+                if (o.w >= 0) v3 = ldg4(vbase + o.w);
+                acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y);
+                acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
+                acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y);
+                acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
+                acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y);
+                acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
+                acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y);
+                acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
+            }
+        }
+        if (lp0 + cl < LP) __syncthreads();  // records are reused by the next pass
+    }
+    if (live) reinterpret_cast<float4 *>(out)[(size_t)pair * LANES + lane] = acc;
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(FastCfg<LANES>::THREADS)
+msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                     const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                     const float *__restrict__ attn, const float *__restrict__ grad_out,
+                     float *__restrict__ grad_value, float *__restrict__ grad_loc,
+                     float *__restrict__ grad_attn,
+                     int S, int M, int L, int P, int LqM, int total_pairs,
+                     int64_t value_batch_stride, int cl)
+{
+    using Cfg = FastCfg<LANES>;
+    __shared__ LevelTable lv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdRec *rec = reinterpret_cast<BwdRec *>(smem_raw);
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(BwdRec) * Cfg::PAIRS * cl);  // [rec][SUBS][3]
+
+    const int tid = threadIdx.x;
+    const int LP = L * P;
+    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const int cell_stride = M * LANES;
+
+    load_level_table(lv, shapes, lsi, L);
+    __syncthreads();
+
+    const int pl = tid / LANES;
+    const int lane = tid - pl * LANES;
+    const int sub = lane >> 2;
+    const int pair = pair0 + pl;
+    const bool live = pair < total_pairs;
+    const float4 *vbase = reinterpret_cast<const float4 *>(value);
+    float4 *gvbase = reinterpret_cast<float4 *>(grad_value);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        const int b = pair / LqM;
+        const int m = pair % M;
+        vbase = reinterpret_cast<const float4 *>(value + (int64_t)b * value_batch_stride) + m * LANES + lane;
+        gvbase = reinterpret_cast<float4 *>(grad_value + (int64_t)b * S * M * (LANES * 4)) + m * LANES + lane;
+        g = ldg4(reinterpret_cast<const float4 *>(grad_out) + (size_t)pair * LANES + lane);
+    }
+
+    for (int lp0 = 0; lp0 < LP; lp0 += cl) {
+        const int n = min(cl, LP - lp0);
+        // ---- phase 1: one thread per sample ----
+        for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
+            const int spl = i / n;
+            const int lp = lp0 + (i - spl * n);
+            const int sp = pair0 + spl;
+            BwdRec r;
+            r.off = make_int4(-1, -1, -1, -1);
+            r.lx = 0.f; r.ly = 0.f; r.a = 0.f; r.level = 0;
+            if (sp < total_pairs) {
+                const size_t si = (size_t)sp * LP + lp;
+                const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
+                const int l = lp / P;
+                const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
+                r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
+                r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
+                r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
+                r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
+                r.lx = s.lx; r.ly = s.ly; r.a = __ldg(attn + si); r.level = l;
+            }
+            rec[i] = r;
+        }
+        __syncthreads();
+        // ---- phase 2: gather + scatter; every thread runs it (full-mask shuffles) ----
+        {
+            const BwdRec *my = rec + pl * n;
+            float *mypart = part + (size_t)(pl * n) * (Cfg::SUBS * 3) + sub * 3;
+#pragma unroll 2
+            for (int j = 0; j < n; ++j) {
+                const int4 o = my[j].off;
+                const float lx = my[j].lx, ly = my[j].ly, a = my[j].a;
+                const float hx = 1.f - lx, hy = 1.f - ly;
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+                if (o.x >= 0) v0 = ldg4(vbase + o.x);
+                if (o.y >= 0) v1 = ldg4(vbase + o.y);
+                if (o.z >= 0) v2 = ldg4(vbase + o.z);
+                if (o.w >= 0) v3 = ldg4(vbase + o.w);
+                // grad_value: w_k * A * G  (vector reductions, one per corner per lane)
+                const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+                const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
+                if (o.x >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.x), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
+                if (o.y >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.y), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
+                if (o.z >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.z), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
+                if (o.w >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.w), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+                // per-sample scalars: <G,val>, <G,dval/dx>, <G,dval/dy> over this lane's channels
+                float4 val, dxv, dyv;
+                val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+                val.y = w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+                val.z = w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+                val.w = w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+                dxv.x = hy * (v1.x - v0.x) + ly * (v3.x - v2.x);
+                dxv.y = hy * (v1.y - v0.y) + ly * (v3.y - v2.y);
+                dxv.z = hy * (v1.z - v0.z) + ly * (v3.z - v2.z);
+                dxv.w = hy * (v1.w - v0.w) + ly * (v3.w - v2.w);
+                dyv.x = hx * (v2.x - v0.x) + lx * (v3.x - v1.x);
+                dyv.y = hx * (v2.y - v0.y) + lx * (v3.y - v1.y);
+                dyv.z = hx * (v2.z - v0.z) + lx * (v3.z - v1.z);
+                dyv.w = hx * (v2.w - v0.w) + lx * (v3.w - v1.w);
+                float pa = dot4(g, val), px = dot4(g, dxv), py = dot4(g, dyv);
+                pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+                px += __shfl_xor_sync(0xffffffffu, px, 1);
+                py += __shfl_xor_sync(0xffffffffu, py, 1);
+                pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+                px += __shfl_xor_sync(0xffffffffu, px, 2);
+                py += __shfl_xor_sync(0xffffffffu, py, 2);
+                if ((lane & 3) == 0) {
+                    float *dst = mypart + j * (Cfg::SUBS * 3);
+                    dst[0] = pa; dst[1] = px; dst[2] = py;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: one thread per sample finishes grad_attn / grad_loc ----
+        for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
+            const int spl = i / n;
+            const int lp = lp0 + (i - spl * n);
+            const int sp = pair0 + spl;
+            if (sp < total_pairs) {
+                const float *p = part + (size_t)i * (Cfg::SUBS * 3);
+                float pa = 0.f, px = 0.f, py = 0.f;
+#pragma unroll
+                for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
+                const BwdRec r = rec[i];
+                const size_t si = (size_t)sp * LP + lp;
+                grad_attn[si] = pa;
+                reinterpret_cast<float2 *>(grad_loc)[si] =
+                    make_float2((float)lv.W[r.level] * r.a * px, (float)lv.H[r.level] * r.a * py);
+            }
+        }
+        if (lp0 + cl < LP) __syncthreads();
+    }
+}
+
+bool fast_path_ok(const OpDims &d)
+{
+    if (d.D % 16 != 0 || d.D > 128) return false;
+    if (d.L > kMaxLevels) return false;
+    if (d.value_batch_stride % 4 != 0) return false;
+    // in-kernel 32-bit indices: float4 cell offsets, pair and sample counters
+    if ((int64_t)d.S * d.M * (d.D / 4) >= (int64_t)INT32_MAX) return false;
+    if ((int64_t)d.N * d.Lq * d.M >= (int64_t)INT32_MAX / 64) return false;
+    return true;
+}
+
+template <int LANES>
+static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                   const float *loc, const float *attn, float *out,
+                                   const OpDims &d, cudaStream_t stream)
+{
+    using Cfg = FastCfg<LANES>;
+    const int total_pairs = d.N * d.Lq * d.M;
+    const int LP = d.L * d.P;
+    const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
+    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    const size_t smem = sizeof(FwdRec) * Cfg::PAIRS * cl;
+    msda_fwd_fast_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(
+        value, shapes, lsi, loc, attn, out, d.M, d.L, d.P, d.Lq * d.M, total_pairs,
+        d.value_batch_stride, cl);
+    return cudaGetLastError();
+}
+
+template <int LANES>
+static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                   const float *loc, const float *attn, const float *grad_out,
+                                   float *grad_value, float *grad_loc, float *grad_attn,
+                                   const OpDims &d, cudaStream_t stream)
+{
+    using Cfg = FastCfg<LANES>;
+    const int total_pairs = d.N * d.Lq * d.M;
+    const int LP = d.L * d.P;
+    const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
+    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    const size_t smem = (sizeof(BwdRec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * cl;
+    msda_bwd_fast_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(
+        value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d.S, d.M, d.L,
+        d.P, d.Lq * d.M, total_pairs, d.value_batch_stride, cl);
+    return cudaGetLastError();
+}
+
+#define MSDA_DISPATCH_LANES(D, CALL)                 \
+    switch ((D) / 4) {                               \
+        case 4: return CALL(4);                      \
+        case 8: return CALL(8);                      \
+        case 12: return CALL(12);                    \
+        case 16: return CALL(16);                    \
+        case 20: return CALL(20);                    \
+        case 24: return CALL(24);                    \
+        case 28: return CALL(28);                    \
+        case 32: return CALL(32);                    \
+        default: return cudaErrorInvalidValue;       \
+    }
+
+cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                    const float *loc, const float *attn, float *out,
+                                    const OpDims &d, cudaStream_t stream)
+{
+    if (d.N * d.Lq * d.M == 0) return cudaSuccess;
+#define CALL(LN) launch_fwd_fast<LN>(value, shapes, lsi, loc, attn, out, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_backward_fast_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                     const float *loc, const float *attn, const float *grad_out,
+                                     float *grad_value, float *grad_loc, float *grad_attn,
+                                     const OpDims &d, cudaStream_t stream)
+{
+    if (d.N * d.Lq * d.M == 0) return cudaSuccess;
+#define CALL(LN) \
+    launch_bwd_fast<LN>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+// ------------------------------------------------------------------------------------------
+// GENERIC path (float / double, any D)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
+                        const int64_t *__restrict__ lsi, const T *__restrict__ loc,
+                        const T *__restrict__ attn, T *__restrict__ out,
+                        int M, int D, int L, int P, int Lq, int64_t total, int64_t value_batch_stride)
+{
+    __shared__ LevelTable lv;
+    load_level_table(lv, shapes, lsi, L);
+    __syncthreads();
+    const int LP = L * P;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % D);
+        const int64_t pair = idx / D;
+        const int m = (int)(pair % M);
+        const int64_t b = pair / ((int64_t)Lq * M);
+        const T *vb = value + b * value_batch_stride + (int64_t)m * D + c;
+        const int64_t cs = (int64_t)M * D;
+        T acc = (T)0;
+        for (int lp = 0; lp < LP; ++lp) {
+            const int l = lp / P;
+            const int64_t si = pair * LP + lp;
+            const Sample<T> s = make_sample<T>(loc[2 * si], loc[2 * si + 1], lv.H[l], lv.W[l], lv.start[l]);
+            const T hx = (T)1 - s.lx, hy = (T)1 - s.ly;
+            T val = (T)0;
+            if (s.cell[0] >= 0) val += hy * hx * vb[s.cell[0] * cs];
+            if (s.cell[1] >= 0) val += hy * s.lx * vb[s.cell[1] * cs];
+            if (s.cell[2] >= 0) val += s.ly * hx * vb[s.cell[2] * cs];
+            if (s.cell[3] >= 0) val += s.ly * s.lx * vb[s.cell[3] * cs];
+            acc += attn[si] * val;
+        }
+        out[idx] = acc;
+    }
+}
+
+// one warp per (n,q,m) pair; lanes stride over channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_bwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
+                        const int64_t *__restrict__ lsi, const T *__restrict__ loc,
+                        const T *__restrict__ attn, const T *__restrict__ grad_out,
+                        T *__restrict__ grad_value, T *__restrict__ grad_loc,
+                        T *__restrict__ grad_attn,
+                        int S, int M, int D, int L, int P, int Lq, int64_t total_pairs,
+                        int64_t value_batch_stride)
+{
+    __shared__ LevelTable lv;
+    load_level_table(lv, shapes, lsi, L);
+    __syncthreads();
+    const int LP = L * P;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t cs = (int64_t)M * D;
+    for (int64_t pair = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pair < total_pairs;
+         pair += (int64_t)gridDim.x * warps_per_block) {
+        const int m = (int)(pair % M);
+        const int64_t b = pair / ((int64_t)Lq * M);
+        const T *vb = value + b * value_batch_stride + (int64_t)m * D;
+        T *gvb = grad_value + b * (int64_t)S * M * D + (int64_t)m * D;
+        const T *g = grad_out + pair * D;
+        for (int lp = 0; lp < LP; ++lp) {
+            const int l = lp / P;
+            const int64_t si = pair * LP + lp;
+            const Sample<T> s = make_sample<T>(loc[2 * si], loc[2 * si + 1], lv.H[l], lv.W[l], lv.start[l]);
+            const T a = attn[si];
+            const T hx = (T)1 - s.lx, hy = (T)1 - s.ly;
+            const T w0 = hy * hx, w1 = hy * s.lx, w2 = s.ly * hx, w3 = s.ly * s.lx;
+            T pa = (T)0, px = (T)0, py = (T)0;
+            for (int c = lane; c < D; c += 32) {
+                const T gc = g[c];
+                const T v0 = s.cell[0] >= 0 ? vb[s.cell[0] * cs + c] : (T)0;
+                const T v1 = s.cell[1] >= 0 ? vb[s.cell[1] * cs + c] : (T)0;
+                const T v2 = s.cell[2] >= 0 ? vb[s.cell[2] * cs + c] : (T)0;
+                const T v3 = s.cell[3] >= 0 ? vb[s.cell[3] * cs + c] : (T)0;
+                const T ga = gc * a;
+                if (s.cell[0] >= 0) atomicAdd(gvb + s.cell[0] * cs + c, w0 * ga);
+                if (s.cell[1] >= 0) atomicAdd(gvb + s.cell[1] * cs + c, w1 * ga);
+                if (s.cell[2] >= 0) atomicAdd(gvb + s.cell[2] * cs + c, w2 * ga);
+                if (s.cell[3] >= 0) atomicAdd(gvb + s.cell[3] * cs + c, w3 * ga);
+                pa += gc * (w0 * v0 + w1 * v1 + w2 * v2 + w3 * v3);
+                px += gc * (hy * (v1 - v0) + s.ly * (v3 - v2));
+                py += gc * (hx * (v2 - v0) + s.lx * (v3 - v1));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                px += __shfl_xor_sync(0xffffffffu, px, o);
+                py += __shfl_xor_sync(0xffffffffu, py, o);
+            }
+            if (lane == 0) {
+                grad_attn[si] = pa;
+                grad_loc[2 * si] = (T)lv.W[l] * a * px;
+                grad_loc[2 * si + 1] = (T)lv.H[l] * a * py;
+            }
+        }
+    }
+}
+
+template <typename T>
+cudaError_t launch_forward_generic(const T *value, const int64_t *shapes, const int64_t *lsi,
+                                   const T *loc, const T *attn, T *out, const OpDims &d,
+                                   cudaStream_t stream)
+{
+    const int64_t total = (int64_t)d.N * d.Lq * d.M * d.D;
+    if (total == 0) return cudaSuccess;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < 148 * 64 ? blocks : 148 * 64);
+    msda_fwd_generic_kernel<T><<<grid, 256, 0, stream>>>(value, shapes, lsi, loc, attn, out, d.M, d.D,
+                                                         d.L, d.P, d.Lq, total, d.value_batch_stride);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_backward_generic(const T *value, const int64_t *shapes, const int64_t *lsi,
+                                    const T *loc, const T *attn, const T *grad_out,
+                                    T *grad_value, T *grad_loc, T *grad_attn, const OpDims &d,
+                                    cudaStream_t stream)
+{
+    const int64_t total_pairs = (int64_t)d.N * d.Lq * d.M;
+    if (total_pairs == 0) return cudaSuccess;
+    const int64_t blocks = (total_pairs + 7) / 8;
+    const int grid = (int)(blocks < 148 * 64 ? blocks : 148 * 64);
+    msda_bwd_generic_kernel<T><<<grid, 256, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out,
+                                                         grad_value, grad_loc, grad_attn, d.S, d.M,
+                                                         d.D, d.L, d.P, d.Lq, total_pairs,
+                                                         d.value_batch_stride);
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_forward_generic<float>(const float *, const int64_t *, const int64_t *,
+                                                   const float *, const float *, float *,
+                                                   const OpDims &, cudaStream_t);
+template cudaError_t launch_forward_generic<double>(const double *, const int64_t *, const int64_t *,
+                                                    const double *, const double *, double *,
+                                                    const OpDims &, cudaStream_t);
+template cudaError_t launch_backward_generic<float>(const float *, const int64_t *, const int64_t *,
+                                                    const float *, const float *, const float *,
+                                                    float *, float *, float *, const OpDims &,
+                                                    cudaStream_t);
+template cudaError_t launch_backward_generic<double>(const double *, const int64_t *, const int64_t *,
+                                                     const double *, const double *, const double *,
+                                                     double *, double *, double *, const OpDims &,
+                                                     cudaStream_t);
+
+}  // namespace msda

@@ -1,0 +1,397 @@
+// Fused Snipper snippet attention: one launch per transformer layer (sm_100a, fp32).
+//
+// Replaces the Python per-frame loop of the reference module
+// (models/ops/modules/ms_deform_attn.py:126-225): for every query frame t1 the reference
+// re-runs the sampling_offsets / attention_weights GEMMs per neighbour frame t2, a softmax over
+// (levels, points, neighbour frames), two .contiguous() copies and one op launch per (t1,t2)
+// pair (10 pairs at T=4), then stacks and sums.  Because every frame slot holds the SAME Linear
+// (ms_deform_attn.py:68-71) the logits/offsets do not depend on t2, so
+//     softmax_{l,p,k}(logits)[.., j] = softmax_{l,p}(logits) / k      (k = #neighbour frames)
+// and the whole loop collapses to: per (n,t1,q,m) set up L*P samples ONCE
+// (loc = ref + offset/(W,H); A = softmax/k) and gather them from each of the k neighbour
+// frames of `value`, accumulating in registers.
+//
+// Same CTA organisation as the per-call fast path (msda_percall.cu): PAIRS pairs x LANES lanes,
+// phase 1 = one thread per sample (here it also does the softmax and the offset normalisation),
+// phase 2 = lanes gather 128-bit channel chunks; backward adds vector reductions into
+// grad_value, 4-lane shuffles for the per-sample scalars and the softmax backward in phase 3.
+#include "msda_common.cuh"
+#include "msda_internal.h"
+
+namespace msda {
+
+constexpr int kSnippetMaxLP = 32;
+
+template <int LANES>
+struct SnipCfg {
+    static constexpr int PAIRS = LANES <= 16 ? 16 : 8;
+    static constexpr int THREADS = PAIRS * LANES;
+    static constexpr int SUBS = LANES / 4;
+    static_assert(LANES % 4 == 0 && THREADS % 32 == 0, "lane groups must tile warps");
+};
+
+struct __align__(16) SnipFwdRec {
+    int4 off;
+    float4 w;
+};
+
+struct __align__(16) SnipBwdRec {
+    int4 off;
+    float lx, ly, a;
+    int level;
+};
+
+__device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo, int &hi)
+{
+    // reference ms_deform_attn.py:137-140 (observed frames) and :189,201 (future frames)
+    if (t1 < n_frame) { lo = max(t1 - 1, 0); hi = min(t1 + 1, n_frame - 1); }
+    else { lo = 0; hi = T2 - 1; }
+}
+
+// softmax over the L*P logits of one pair, evaluated for entry lp, divided by k
+__device__ __forceinline__ float pair_softmax(const float *__restrict__ z, int LP, int lp, float inv_k)
+{
+    float mx = -INFINITY;
+    for (int j = 0; j < LP; ++j) mx = fmaxf(mx, __ldg(z + j));
+    float sum = 0.f;
+    for (int j = 0; j < LP; ++j) sum += expf(__ldg(z + j) - mx);
+    return expf(__ldg(z + lp) - mx) / sum * inv_k;
+}
+
+struct PairCoord { int n, t1, q, m; };
+
+__device__ __forceinline__ PairCoord split_pair(int pair, int M, int Lq, int T1)
+{
+    PairCoord c;
+    c.m = pair % M; pair /= M;
+    c.q = pair % Lq; pair /= Lq;
+    c.t1 = pair % T1;
+    c.n = pair / T1;
+    return c;
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(SnipCfg<LANES>::THREADS)
+msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                        const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
+                        const float *__restrict__ logits, const float *__restrict__ ref,
+                        float *__restrict__ out, SnippetDims d, int total_pairs)
+{
+    using Cfg = SnipCfg<LANES>;
+    __shared__ LevelTable lv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SnipFwdRec *rec = reinterpret_cast<SnipFwdRec *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int LP = d.L * d.P;
+    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const int cell_stride = d.M * LANES;
+
+    load_level_table(lv, shapes, lsi, d.L);
+    __syncthreads();
+
+    // ---- phase 1: one thread per sample ----
+    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
+        const int spl = i / LP;
+        const int lp = i - spl * LP;
+        const int sp = pair0 + spl;
+        SnipFwdRec r;
+        r.off = make_int4(-1, -1, -1, -1);
+        r.w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sp < total_pairs) {
+            const PairCoord c = split_pair(sp, d.M, d.Lq, d.T1);
+            int lo, hi;
+            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+            const float a = pair_softmax(logits + (size_t)sp * LP, LP, lp, 1.f / (float)(hi - lo + 1));
+            const int l = lp / d.P;
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + (size_t)sp * LP + lp);
+            const float *rp = ref + c.n * d.ref_stride_n + c.t1 * d.ref_stride_t + ((int64_t)c.q * d.L + l) * 2;
+            const float u = __ldg(rp) + o.x / (float)lv.W[l];
+            const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
+            const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
+            const float hx = 1.f - s.lx, hy = 1.f - s.ly;
+            r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
+            r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
+            r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
+            r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
+            r.w = make_float4(hy * hx * a, hy * s.lx * a, s.ly * hx * a, s.ly * s.lx * a);
+        }
+        rec[i] = r;
+    }
+    __syncthreads();
+
+    // ---- phase 2: gather from every neighbour frame ----
+    const int pl = tid / LANES;
+    const int lane = tid - pl * LANES;
+    const int pair = pair0 + pl;
+    if (pair >= total_pairs) return;
+    const PairCoord c = split_pair(pair, d.M, d.Lq, d.T1);
+    int lo, hi;
+    frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+    const float4 *vframe = reinterpret_cast<const float4 *>(value + c.n * d.value_stride_n + lo * d.value_stride_t) +
+                           c.m * LANES + lane;
+    const int64_t fstride = d.value_stride_t / 4;  // float4 units
+    const int nf = hi - lo + 1;
+    const SnipFwdRec *my = rec + pl * LP;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int j = 0; j < LP; ++j) {
+        const int4 o = my[j].off;
+        const float4 w = my[j].w;
+        const float4 *vb = vframe;
+        for (int f = 0; f < nf; ++f, vb += fstride) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+            if (o.x >= 0) v0 = ldg4(vb + o.x);
+            if (o.y >= 0) v1 = ldg4(vb + o.y);
+            if (o.z >= 0) v2 = ldg4(vb + o.z);
+            if (o.w >= 0) v3 = ldg4(vb + o.w);
+            acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y);
+            acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
+            acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y);
+            acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
+            acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y);
+            acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
+            acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y);
+            acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
+        }
+    }
+    reinterpret_cast<float4 *>(out)[(size_t)pair * LANES + lane] = acc;
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(SnipCfg<LANES>::THREADS)
+msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                        const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
+                        const float *__restrict__ logits, const float *__restrict__ ref,
+                        const float *__restrict__ grad_out, float *__restrict__ grad_value,
+                        float *__restrict__ grad_offsets, float *__restrict__ grad_logits,
+                        SnippetDims d, int total_pairs)
+{
+    using Cfg = SnipCfg<LANES>;
+    __shared__ LevelTable lv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SnipBwdRec *rec = reinterpret_cast<SnipBwdRec *>(smem_raw);
+    const int LP = d.L * d.P;
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(SnipBwdRec) * Cfg::PAIRS * LP);  // [rec][SUBS][3]
+
+    const int tid = threadIdx.x;
+    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const int cell_stride = d.M * LANES;
+
+    load_level_table(lv, shapes, lsi, d.L);
+    __syncthreads();
+
+    // ---- phase 1 ----
+    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
+        const int spl = i / LP;
+        const int lp = i - spl * LP;
+        const int sp = pair0 + spl;
+        SnipBwdRec r;
+        r.off = make_int4(-1, -1, -1, -1);
+        r.lx = 0.f; r.ly = 0.f; r.a = 0.f; r.level = 0;
+        if (sp < total_pairs) {
+            const PairCoord c = split_pair(sp, d.M, d.Lq, d.T1);
+            int lo, hi;
+            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+            const int l = lp / d.P;
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + (size_t)sp * LP + lp);
+            const float *rp = ref + c.n * d.ref_stride_n + c.t1 * d.ref_stride_t + ((int64_t)c.q * d.L + l) * 2;
+            const float u = __ldg(rp) + o.x / (float)lv.W[l];
+            const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
+            const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
+            r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
+            r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
+            r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
+            r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
+            r.lx = s.lx; r.ly = s.ly; r.level = l;
+            r.a = pair_softmax(logits + (size_t)sp * LP, LP, lp, 1.f / (float)(hi - lo + 1));
+        }
+        rec[i] = r;
+    }
+    __syncthreads();
+
+    // ---- phase 2: every thread participates (full-mask shuffles) ----
+    {
+        const int pl = tid / LANES;
+        const int lane = tid - pl * LANES;
+        const int sub = lane >> 2;
+        const int pair = pair0 + pl;
+        const bool live = pair < total_pairs;
+        const float4 *vframe = reinterpret_cast<const float4 *>(value);
+        float4 *gvframe = reinterpret_cast<float4 *>(grad_value);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        int nf = 0;
+        if (live) {
+            const PairCoord c = split_pair(pair, d.M, d.Lq, d.T1);
+            int lo, hi;
+            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+            nf = hi - lo + 1;
+            vframe = reinterpret_cast<const float4 *>(value + c.n * d.value_stride_n + lo * d.value_stride_t) +
+                     c.m * LANES + lane;
+            gvframe = reinterpret_cast<float4 *>(grad_value + ((int64_t)c.n * d.T2 + lo) * d.S * d.M * (LANES * 4)) +
+                      c.m * LANES + lane;
+            g = ldg4(reinterpret_cast<const float4 *>(grad_out) + (size_t)pair * LANES + lane);
+        }
+        const int64_t fstride = d.value_stride_t / 4;
+        const int64_t gfstride = (int64_t)d.S * d.M * LANES;
+        const SnipBwdRec *my = rec + pl * LP;
+        float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
+        for (int j = 0; j < LP; ++j) {
+            const int4 o = my[j].off;
+            const float lx = my[j].lx, ly = my[j].ly, a = my[j].a;
+            const float hx = 1.f - lx, hy = 1.f - ly;
+            const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
+            const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+            float pa = 0.f, px = 0.f, py = 0.f;
+            const float4 *vb = vframe;
+            float4 *gvb = gvframe;
+            for (int f = 0; f < nf; ++f, vb += fstride, gvb += gfstride) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+                if (o.x >= 0) v0 = ldg4(vb + o.x);
+                if (o.y >= 0) v1 = ldg4(vb + o.y);
+                if (o.z >= 0) v2 = ldg4(vb + o.z);
+                if (o.w >= 0) v3 = ldg4(vb + o.w);
+                if (o.x >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.x), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
+                if (o.y >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.y), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
+                if (o.z >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.z), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
+                if (o.w >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.w), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+                float4 val, dxv, dyv;
+                val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+                val.y = w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+                val.z = w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+                val.w = w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+                dxv.x = hy * (v1.x - v0.x) + ly * (v3.x - v2.x);
+                dxv.y = hy * (v1.y - v0.y) + ly * (v3.y - v2.y);
+                dxv.z = hy * (v1.z - v0.z) + ly * (v3.z - v2.z);
+                dxv.w = hy * (v1.w - v0.w) + ly * (v3.w - v2.w);
+                dyv.x = hx * (v2.x - v0.x) + lx * (v3.x - v1.x);
+                dyv.y = hx * (v2.y - v0.y) + lx * (v3.y - v1.y);
+                dyv.z = hx * (v2.z - v0.z) + lx * (v3.z - v1.z);
+                dyv.w = hx * (v2.w - v0.w) + lx * (v3.w - v1.w);
+                pa += dot4(g, val); px += dot4(g, dxv); py += dot4(g, dyv);
+            }
+            pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+            px += __shfl_xor_sync(0xffffffffu, px, 1);
+            py += __shfl_xor_sync(0xffffffffu, py, 1);
+            pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+            px += __shfl_xor_sync(0xffffffffu, px, 2);
+            py += __shfl_xor_sync(0xffffffffu, py, 2);
+            if ((lane & 3) == 0) {
+                float *dst = mypart + j * (Cfg::SUBS * 3);
+                dst[0] = pa; dst[1] = px; dst[2] = py;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: per-sample finish + softmax backward ----
+    // dL/dz_i = A_i * (gA_i - k * sum_j gA_j A_j)   with A = softmax/k, gA_i = <G, val_i> summed over frames
+    float pa_i[(Cfg::PAIRS * kSnippetMaxLP + Cfg::THREADS - 1) / Cfg::THREADS];
+    int it = 0;
+    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS, ++it) {
+        const float *p = part + (size_t)i * (Cfg::SUBS * 3);
+        float pa = 0.f, px = 0.f, py = 0.f;
+#pragma unroll
+        for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
+        pa_i[it] = pa;
+        const SnipBwdRec r = rec[i];
+        const int sp = pair0 + i / LP;
+        if (sp < total_pairs) {
+            // loc = ref + off/(W,H) and x = loc*W - 0.5  =>  dx/doff_x = 1: the W factor of the
+            // per-call grad_loc (W*A*px) cancels against the 1/W of the normalisation.
+            reinterpret_cast<float2 *>(grad_offsets)[(size_t)pair0 * LP + i] = make_float2(r.a * px, r.a * py);
+        }
+        part[(size_t)i * (Cfg::SUBS * 3)] = pa * r.a;  // own slot only
+    }
+    __syncthreads();
+    it = 0;
+    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS, ++it) {
+        const int spl = i / LP;
+        const int sp = pair0 + spl;
+        if (sp < total_pairs) {
+            const PairCoord c = split_pair(sp, d.M, d.Lq, d.T1);
+            int lo, hi;
+            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+            float dot = 0.f;
+            for (int j = 0; j < LP; ++j) dot += part[(size_t)(spl * LP + j) * (Cfg::SUBS * 3)];
+            grad_logits[(size_t)pair0 * LP + i] = rec[i].a * (pa_i[it] - (float)(hi - lo + 1) * dot);
+        }
+    }
+}
+
+bool snippet_ok(const SnippetDims &d)
+{
+    if (d.D % 16 != 0 || d.D > 128) return false;
+    if (d.L > kMaxLevels || d.L * d.P > kSnippetMaxLP) return false;
+    if (d.value_stride_n % 4 != 0 || d.value_stride_t % 4 != 0) return false;
+    if ((int64_t)d.S * d.M * (d.D / 4) >= (int64_t)INT32_MAX) return false;
+    if ((int64_t)d.N * d.T1 * d.Lq * d.M >= (int64_t)INT32_MAX / 64) return false;
+    return true;
+}
+
+template <int LANES>
+static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                   const float *offsets, const float *logits, const float *ref,
+                                   float *out, const SnippetDims &d, cudaStream_t stream)
+{
+    using Cfg = SnipCfg<LANES>;
+    const int total_pairs = d.N * d.T1 * d.Lq * d.M;
+    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    const size_t smem = sizeof(SnipFwdRec) * Cfg::PAIRS * d.L * d.P;
+    msda_snippet_fwd_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets, logits,
+                                                                        ref, out, d, total_pairs);
+    return cudaGetLastError();
+}
+
+template <int LANES>
+static cudaError_t launch_snip_bwd(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                   const float *offsets, const float *logits, const float *ref,
+                                   const float *grad_out, float *grad_value, float *grad_offsets,
+                                   float *grad_logits, const SnippetDims &d, cudaStream_t stream)
+{
+    using Cfg = SnipCfg<LANES>;
+    const int total_pairs = d.N * d.T1 * d.Lq * d.M;
+    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    const size_t smem = (sizeof(SnipBwdRec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
+    msda_snippet_bwd_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(
+        value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, total_pairs);
+    return cudaGetLastError();
+}
+
+#define MSDA_DISPATCH_LANES(D, CALL)                 \
+    switch ((D) / 4) {                               \
+        case 4: return CALL(4);                      \
+        case 8: return CALL(8);                      \
+        case 12: return CALL(12);                    \
+        case 16: return CALL(16);                    \
+        case 20: return CALL(20);                    \
+        case 24: return CALL(24);                    \
+        case 28: return CALL(28);                    \
+        case 32: return CALL(32);                    \
+        default: return cudaErrorInvalidValue;       \
+    }
+
+cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes,
+                                       const int64_t *lsi, const float *offsets,
+                                       const float *logits, const float *ref, float *out,
+                                       const SnippetDims &d, cudaStream_t stream)
+{
+#define CALL(LN) launch_snip_fwd<LN>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_snippet_backward_f32(const float *value, const int64_t *shapes,
+                                        const int64_t *lsi, const float *offsets,
+                                        const float *logits, const float *ref,
+                                        const float *grad_out, float *grad_value,
+                                        float *grad_offsets, float *grad_logits,
+                                        const SnippetDims &d, cudaStream_t stream)
+{
+#define CALL(LN) \
+    launch_snip_bwd<LN>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+}  // namespace msda

@@ -1,0 +1,170 @@
+"""``MSDeformAttn`` -- drop-in for the reference's Snipper-modified attention module
+(models/ops/modules/ms_deform_attn.py:37-243).
+
+Same constructor signature (including the reference's ``use_pytroch_deform`` spelling), same
+``forward`` contract, same parameter names / state-dict keys
+(``sampling_offsets.{i}``, ``attention_weights.{i}``, ``value_proj``, ``output_proj``; the frame
+slots alias ONE Linear each, :68-71), same initialisation (:78-97), so checkpoints load and
+``models/deformable_transformer.py`` constructs and calls it unchanged (:178, :251-252, :202, :292).
+
+What differs is the execution:
+
+* fused path (default): offsets and logits are computed ONCE for all query frames (the
+  reference recomputes the same two GEMMs for every (t1,t2) pair -- 20 GEMMs per layer at T=4,
+  only 2 distinct), then ONE kernel launch per layer (``snipper_b200::snippet_forward``) does the
+  offset normalisation, the softmax over levels x points x neighbour frames and the gather from
+  all neighbour frames.  No ``.contiguous()`` copies, no stack+sum, no host sync (the
+  reference's shape assert at :112 synchronises the stream every call).
+* per-call path (``fused=False``, or when the frame slots do not alias / shapes are outside the
+  fused kernels' range): the reference's loop, one ``MSDeformAttnFunction`` call per (t1,t2).
+
+``use_pytroch_deform`` is accepted and ignored: there is no PyTorch/CPU implementation in this
+package -- the CUDA kernels always run.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..functions import MSDeformAttnFunction
+
+
+def neighbour_frames(t1, n_frame, n_src_frames):
+    """Source frames a query frame attends to (reference :137-140 observed, :189/:201 future)."""
+    if t1 < n_frame:
+        return [t for t in (t1 - 1, t1, t1 + 1) if 0 <= t < n_frame]
+    return list(range(n_src_frames))
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, n_frame=4,
+                 mode="encoder", use_pytroch_deform=False, attention_vis=False):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        assert mode in ("encoder", "decoder")
+        self.im2col_step = 64
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+        self.n_frame = n_frame
+        self.use_pytroch_deform = use_pytroch_deform  # kept for signature parity; ignored
+        self.mode = mode
+        self.attention_vis = attention_vis
+        self.fused = True
+
+        offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.sampling_offsets = nn.ModuleList([offsets for _ in range(n_frame)])
+        weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.attention_weights = nn.ModuleList([weights for _ in range(n_frame)])
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # head h looks along angle 2*pi*h/M, scaled so the larger component is 1; point p sits
+        # (p+1) pixels out; attention starts uniform (reference :78-97)
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        theta = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        direction = torch.stack([theta.cos(), theta.sin()], -1)
+        direction = direction / direction.abs().max(-1, keepdim=True)[0]
+        steps = torch.arange(1, P + 1, dtype=torch.float32).view(1, 1, P, 1)
+        bias = (direction.view(M, 1, 1, 2) * steps).expand(M, L, P, 2).reshape(-1)
+        with torch.no_grad():
+            for lin in self.sampling_offsets:
+                lin.weight.zero_()
+                lin.bias.copy_(bias)
+            for lin in self.attention_weights:
+                lin.weight.zero_()
+                lin.bias.zero_()
+            nn.init.xavier_uniform_(self.value_proj.weight)
+            self.value_proj.bias.zero_()
+            nn.init.xavier_uniform_(self.output_proj.weight)
+            self.output_proj.bias.zero_()
+
+    # -------------------------------------------------------------------------------------
+    def _slots_aliased(self):
+        so, aw = self.sampling_offsets, self.attention_weights
+        return all(m is so[0] for m in so) and all(m is aw[0] for m in aw)
+
+    def _can_fuse(self, query):
+        return (self.fused and self._slots_aliased() and query.is_cuda and
+                ops.snippet_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
+                                      self.n_points, query.dtype))
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
+                input_level_start_index, input_padding_mask=None):
+        """query (N,T1,Lq,C); reference_points (N,T1,Lq,L,2) in [0,1]; input_flatten (N,T2,S,C);
+        input_spatial_shapes (L,2) int64; input_level_start_index (L,) int64;
+        input_padding_mask (N,T2,S,C) bool, True = padding.  Returns (N,T1,Lq,C), plus
+        ``(sampling_locations per t1, attention_weights per t1)`` when ``attention_vis``."""
+        N, T1, Lq, _ = query.shape
+        _, T2, S, _ = input_flatten.shape
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask, 0.0)
+        value = value.view(N, T2, S, M, self.d_model // M)
+
+        if self._can_fuse(query):
+            offsets = self.sampling_offsets[0](query).view(N, T1, Lq, M, L, P, 2)
+            logits = self.attention_weights[0](query).view(N, T1, Lq, M, L, P)
+            out = torch.ops.snipper_b200.snippet_forward(
+                value, input_spatial_shapes, input_level_start_index, offsets, logits,
+                reference_points, self.n_frame)
+            vis = self._vis_fused(offsets, logits, reference_points, input_spatial_shapes, T2) \
+                if self.attention_vis else None
+        else:
+            out, vis = self._forward_per_call(query, reference_points, value, input_spatial_shapes,
+                                              input_level_start_index)
+        out = self.output_proj(out)
+        if self.attention_vis:
+            return out, vis
+        return out
+
+    # -------------------------------------------------------------------------------------
+    def _vis_fused(self, offsets, logits, reference_points, spatial_shapes, T2):
+        """The (detached) tensors the decoder hands to the visualiser (reference :228-233)."""
+        with torch.no_grad():
+            N, T1, Lq, M, L, P, _ = offsets.shape
+            wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(offsets.dtype)
+            loc = reference_points[:, :, :, None, :, None, :] + offsets / wh[None, None, None, None, :, None, :]
+            att = F.softmax(logits.flatten(-2), -1).view(N, T1, Lq, M, L, P)
+            locs, atts = [], []
+            for t1 in range(T1):
+                k = len(neighbour_frames(t1, self.n_frame, T2))
+                locs.append(loc[:, t1].unsqueeze(-2).expand(N, Lq, M, L, P, k, 2))
+                atts.append((att[:, t1] / k).unsqueeze(-1).expand(N, Lq, M, L, P, k))
+        return locs, atts
+
+    def _forward_per_call(self, query, reference_points, value, spatial_shapes, level_start_index):
+        """One op call per (query frame, neighbour frame), as the reference does (:130-225)."""
+        N, T1, Lq, _ = query.shape
+        T2 = value.shape[1]
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1)
+        outs, vis_loc, vis_att = [], [], []
+        for t1 in range(T1):
+            frames = neighbour_frames(t1, self.n_frame, T2)
+            q = query[:, t1]
+            logits = torch.stack([self.attention_weights[t2](q).view(N, Lq, M, L, P) for t2 in frames], -1)
+            att = F.softmax(logits.flatten(-3), -1).view(N, Lq, M, L, P, len(frames))
+            acc, locs = None, []
+            for j, t2 in enumerate(frames):
+                off = self.sampling_offsets[t2](q).view(N, Lq, M, L, P, 2)
+                loc = reference_points[:, t1, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+                if self.attention_vis:
+                    locs.append(loc.detach())
+                # value[:, t2] keeps its batch stride (no copy); loc/att slices are materialised
+                o = MSDeformAttnFunction.apply(value[:, t2], spatial_shapes, level_start_index,
+                                               loc.contiguous(), att[..., j].contiguous(), self.im2col_step)
+                acc = o if acc is None else acc + o
+            outs.append(acc)
+            if self.attention_vis:
+                vis_loc.append(torch.stack(locs, dim=-2))
+                vis_att.append(att.detach())
+        return torch.stack(outs, dim=1), (vis_loc, vis_att)

@@ -1,0 +1,285 @@
+"""torch custom ops over the C ABI (libmsda_b200.so).
+
+PyTorch is plumbing here: it owns device memory and the current stream; all arithmetic happens
+in the hand-written kernels.  Ops (namespace ``snipper_b200``):
+
+  msda_forward / msda_backward          per-call op, the reference's extension functions
+                                        (models/ops/src/vision.cpp:13-16)
+  snippet_forward / snippet_backward    fused per-layer Snipper attention
+                                        (models/ops/modules/ms_deform_attn.py:126-225)
+
+Both forwards carry ``register_autograd`` formulas, so they compose with autograd / DDP as plain
+nodes (no host sync, no unused parameters).
+"""
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import capi
+
+_DTYPES = {torch.float32: capi.MSDA_DTYPE_F32, torch.float64: capi.MSDA_DTYPE_F64}
+
+# process-wide switch for the deterministic (atomics-free) grad_value path
+_deterministic = False
+
+
+def set_deterministic(flag: bool) -> None:
+    """Select the bit-reproducible two-pass backward (north_star: 'deterministic two-pass mode')."""
+    global _deterministic
+    _deterministic = bool(flag)
+
+
+def is_deterministic() -> bool:
+    return _deterministic
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        # reference models/ops/src/ms_deform_attn.h:38,60
+        raise RuntimeError("Not implemented on the CPU" if name == "value" else "%s must be a CUDA tensor" % name)
+
+
+def _require_contiguous(t: Tensor, name: str) -> None:
+    if not t.is_contiguous():
+        # reference models/ops/src/cuda/ms_deform_attn_cuda.cu:28-32
+        raise RuntimeError("%s tensor has to be contiguous" % name)
+
+
+def _value_batch_stride(value: Tensor) -> int:
+    """value (N,S,M,D): the inner three dims must be dense; the batch stride is free."""
+    N, S, M, D = value.shape
+    if N * S * M * D == 0:
+        return 0
+    if value.stride(3) != 1 or value.stride(2) != D or (S > 1 and value.stride(1) != M * D):
+        raise RuntimeError("value tensor has to be contiguous")
+    return value.stride(0) if N > 1 else S * M * D
+
+
+def _check_percall(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    for t, name in ((value, "value"), (spatial_shapes, "spatial_shapes"),
+                    (level_start_index, "level_start_index"), (sampling_loc, "sampling_loc"),
+                    (attn_weight, "attn_weight")):
+        _require_cuda(t, name)
+    for t, name in ((spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                    (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight")):
+        _require_contiguous(t, name)
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError("expected value (N,S,M,D), sampling_loc (N,Lq,M,L,P,2), attn_weight (N,Lq,M,L,P)")
+    if value.dtype not in _DTYPES:
+        raise RuntimeError("ms_deform_attn: unsupported dtype %s (float32 / float64)" % value.dtype)
+    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("value, sampling_loc and attn_weight must share one dtype")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64")
+    N, S, M, D = value.shape
+    Nl, Lq, Ml, L, P, two = sampling_loc.shape
+    if (Nl, Ml, two) != (N, M, 2) or tuple(attn_weight.shape) != (N, Lq, M, L, P):
+        raise RuntimeError("sampling_loc / attn_weight shapes do not match value")
+    if tuple(spatial_shapes.shape) != (L, 2) or level_start_index.numel() != L:
+        raise RuntimeError("spatial_shapes must be (L,2) and level_start_index (L,)")
+    return N, S, M, D, L, Lq, P
+
+
+@torch.library.custom_op("snipper_b200::msda_forward", mutates_args=())
+def msda_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
+                 sampling_loc: Tensor, attn_weight: Tensor, im2col_step: int) -> Tensor:
+    N, S, M, D, L, Lq, P = _check_percall(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    vbs = _value_batch_stride(value)
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        st = capi.lib().msda_forward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+            N, S, M, D, L, Lq, P, vbs, int(im2col_step), _DTYPES[value.dtype], _stream(value.device))
+    capi.check(st, "ms_deform_attn_forward", N, im2col_step)
+    return out
+
+
+@msda_forward.register_fake
+def _(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    N, S, M, D = value.shape
+    return value.new_empty((N, sampling_loc.shape[1], M * D))
+
+
+@torch.library.custom_op("snipper_b200::msda_backward", mutates_args=())
+def msda_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
+                  sampling_loc: Tensor, attn_weight: Tensor, grad_output: Tensor,
+                  im2col_step: int, deterministic: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    N, S, M, D, L, Lq, P = _check_percall(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    _require_cuda(grad_output, "grad_output")
+    _require_contiguous(grad_output, "grad_output")
+    if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError("grad_output must be (N,Lq,M*D) in value's dtype")
+    vbs = _value_batch_stride(value)
+    grad_value = torch.empty((N, S, M, D), dtype=value.dtype, device=value.device)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    flags = capi.MSDA_FLAG_DETERMINISTIC if deterministic else 0
+    dt = _DTYPES[value.dtype]
+    ws, ws_bytes = None, 0
+    with torch.cuda.device(value.device):
+        if deterministic:
+            ws_bytes = capi.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dt, flags)
+            ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=value.device)
+        ws_ptr = 0 if ws is None else (ws.data_ptr() + 255) // 256 * 256
+        st = capi.lib().msda_backward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+            N, S, M, D, L, Lq, P, vbs, int(im2col_step), dt, flags, ws_ptr, ws_bytes,
+            _stream(value.device))
+    capi.check(st, "ms_deform_attn_backward", N, im2col_step)
+    return grad_value, grad_loc, grad_attn
+
+
+@msda_backward.register_fake
+def _(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step, deterministic):
+    return (value.new_empty(value.shape), torch.empty_like(sampling_loc), torch.empty_like(attn_weight))
+
+
+def _msda_setup_context(ctx, inputs, output):
+    value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step = inputs
+    ctx.im2col_step = im2col_step
+    ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+
+
+def _msda_backward_formula(ctx, grad_output):
+    value, spatial_shapes, level_start_index, sampling_loc, attn_weight = ctx.saved_tensors
+    gv, gl, ga = torch.ops.snipper_b200.msda_backward(
+        value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+        grad_output.contiguous(), ctx.im2col_step, _deterministic)
+    return gv, None, None, gl, ga, None
+
+
+msda_forward.register_autograd(_msda_backward_formula, setup_context=_msda_setup_context)
+
+
+# ------------------------------------------------------------------------------------------
+# fused snippet op
+# ------------------------------------------------------------------------------------------
+def snippet_supported(n_heads: int, d_head: int, n_levels: int, n_points: int, dtype) -> bool:
+    """Shapes the fused kernels cover (include/msda_b200.h, msda_snippet_forward)."""
+    return (dtype == torch.float32 and d_head % 16 == 0 and d_head <= 128 and
+            n_levels * n_points <= 32 and n_levels <= 64)
+
+
+def _check_snippet(value, spatial_shapes, level_start_index, offsets, logits, ref, n_frame):
+    for t, name in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                    (offsets, "offsets"), (logits, "logits"), (ref, "reference_points")):
+        _require_cuda(t, name)
+    if value.dim() != 5 or offsets.dim() != 7 or logits.dim() != 6 or ref.dim() != 5:
+        raise RuntimeError("expected value (N,T2,S,M,D), offsets (N,T1,Lq,M,L,P,2), logits (N,T1,Lq,M,L,P), "
+                           "reference_points (N,T1,Lq,L,2)")
+    N, T2, S, M, D = value.shape
+    No, T1, Lq, Mo, L, P, two = offsets.shape
+    if (No, Mo, two) != (N, M, 2) or tuple(logits.shape) != (N, T1, Lq, M, L, P):
+        raise RuntimeError("offsets / logits shapes do not match value")
+    if tuple(ref.shape) != (N, T1, Lq, L, 2) or tuple(spatial_shapes.shape) != (L, 2):
+        raise RuntimeError("reference_points must be (N,T1,Lq,L,2) and spatial_shapes (L,2)")
+    if not snippet_supported(M, D, L, P, value.dtype):
+        raise RuntimeError("fused snippet attention needs float32, D % 16 == 0, D <= 128, L*P <= 32")
+    if any(t.dtype != torch.float32 for t in (offsets, logits, ref)):
+        raise RuntimeError("offsets, logits and reference_points must be float32")
+    if not (0 < n_frame <= T2):
+        raise RuntimeError("n_frame must be in (0, T2]")
+    _require_contiguous(offsets, "offsets")
+    _require_contiguous(logits, "logits")
+    _require_contiguous(spatial_shapes, "spatial_shapes")
+    _require_contiguous(level_start_index, "level_start_index")
+    return N, T2, T1, S, M, D, L, Lq, P
+
+
+def _value_strides5(value):
+    N, T2, S, M, D = value.shape
+    if value.stride(4) != 1 or value.stride(3) != D or (S > 1 and value.stride(2) != M * D):
+        raise RuntimeError("value tensor has to be contiguous in its (S,M,D) dims")
+    st = value.stride(1) if T2 > 1 else S * M * D
+    sn = value.stride(0) if N > 1 else st * T2
+    return sn, st
+
+
+def _ref_strides(ref):
+    """(N,T1,Lq,L,2): inner (Lq,L,2) dense; batch / frame strides free (0 = broadcast)."""
+    N, T1, Lq, L, _ = ref.shape
+    if ref.numel() and (ref.stride(4) != 1 or ref.stride(3) != 2 or (Lq > 1 and ref.stride(2) != 2 * L)):
+        ref = ref.contiguous()
+    return ref, (ref.stride(0) if N > 1 else 0), (ref.stride(1) if T1 > 1 else 0)
+
+
+@torch.library.custom_op("snipper_b200::snippet_forward", mutates_args=())
+def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
+                    offsets: Tensor, logits: Tensor, reference_points: Tensor, n_frame: int) -> Tensor:
+    N, T2, T1, S, M, D, L, Lq, P = _check_snippet(value, spatial_shapes, level_start_index, offsets,
+                                                  logits, reference_points, n_frame)
+    sn, st = _value_strides5(value)
+    ref, rsn, rst = _ref_strides(reference_points)
+    out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        status = capi.lib().msda_snippet_forward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), out.data_ptr(),
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
+            capi.MSDA_DTYPE_F32, _stream(value.device))
+    capi.check(status, "msda_snippet_forward")
+    return out
+
+
+@snippet_forward.register_fake
+def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame):
+    N, T2, S, M, D = value.shape
+    return value.new_empty((N, offsets.shape[1], offsets.shape[2], M * D))
+
+
+@torch.library.custom_op("snipper_b200::snippet_backward", mutates_args=())
+def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
+                     offsets: Tensor, logits: Tensor, reference_points: Tensor, grad_output: Tensor,
+                     n_frame: int) -> Tuple[Tensor, Tensor, Tensor]:
+    N, T2, T1, S, M, D, L, Lq, P = _check_snippet(value, spatial_shapes, level_start_index, offsets,
+                                                  logits, reference_points, n_frame)
+    _require_cuda(grad_output, "grad_output")
+    _require_contiguous(grad_output, "grad_output")
+    sn, st = _value_strides5(value)
+    ref, rsn, rst = _ref_strides(reference_points)
+    grad_value = torch.empty((N, T2, S, M, D), dtype=value.dtype, device=value.device)
+    grad_offsets = torch.empty_like(offsets)
+    grad_logits = torch.empty_like(logits)
+    with torch.cuda.device(value.device):
+        status = capi.lib().msda_snippet_backward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(),
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
+            capi.MSDA_DTYPE_F32, 0, _stream(value.device))
+    capi.check(status, "msda_snippet_backward")
+    return grad_value, grad_offsets, grad_logits
+
+
+@snippet_backward.register_fake
+def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, grad_output, n_frame):
+    return (value.new_empty(value.shape), torch.empty_like(offsets), torch.empty_like(logits))
+
+
+def _snippet_setup_context(ctx, inputs, output):
+    value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame = inputs
+    ctx.n_frame = n_frame
+    ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
+
+
+def _snippet_backward_formula(ctx, grad_output):
+    value, spatial_shapes, level_start_index, offsets, logits, ref = ctx.saved_tensors
+    gv, goff, glog = torch.ops.snipper_b200.snippet_backward(
+        value, spatial_shapes, level_start_index, offsets, logits, ref, grad_output.contiguous(), ctx.n_frame)
+    gref = None
+    if ctx.needs_input_grad[5]:
+        # loc = ref + off/(W,H)  =>  dL/dref = sum_{m,p} dL/dloc = sum_{m,p} dL/doff * (W,H)
+        wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
+        gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
+    return gv, None, None, goff, glog, gref, None
+
+
+snippet_forward.register_autograd(_snippet_backward_formula, setup_context=_snippet_setup_context)
