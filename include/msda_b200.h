@@ -72,6 +72,9 @@ MSDA_API int msda_abi_version(void);
 MSDA_API const char *msda_error_string(int status);
 /* cudaError_t of the last failed launch seen by this thread (0 if none). */
 MSDA_API int msda_last_cuda_error(void);
+/* Optional performance knob (results never depend on it): queries per CTA tile for D = 48.
+ * keys "pairs_d48" (per-call kernels) and "snip_pairs_d48" (fused kernels); value 8, 16 or 32. */
+MSDA_API int msda_set_tuning(const char *key, int value);
 
 /*
  * Forward.  output[n,q,m*D+c] = sum_{l,p} attn[n,q,m,l,p] * bilinear(value_l[n,:,m,c], loc[n,q,m,l,p])

@@ -27,7 +27,7 @@ MSDA_FLAG_ACCUMULATE_VALUE = 2
 
 # every symbol include/msda_b200.h declares
 EXPORTS = (
-    "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_forward",
+    "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_set_tuning", "msda_forward",
     "msda_backward", "msda_backward_workspace_bytes", "msda_snippet_forward",
     "msda_snippet_backward",
 )
@@ -59,6 +59,8 @@ def lib():
     L.msda_error_string.argtypes = [i32]
     L.msda_last_cuda_error.restype = i32
     L.msda_last_cuda_error.argtypes = []
+    L.msda_set_tuning.restype = i32
+    L.msda_set_tuning.argtypes = [ctypes.c_char_p, i32]
     L.msda_forward.restype = i32
     L.msda_forward.argtypes = [vp] * 6 + [i32] * 7 + [i64, i32, i32, vp]
     L.msda_backward.restype = i32

@@ -4,6 +4,13 @@
 #include "../../include/msda_b200.h"
 #include "msda_internal.h"
 
+#include <string.h>
+
+namespace msda {
+extern int g_pairs_d48;
+extern int g_snip_pairs_d48;
+}  // namespace msda
+
 namespace {
 
 thread_local int g_last_cuda_error = 0;
@@ -46,6 +53,15 @@ extern "C" {
 int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 
 int msda_last_cuda_error(void) { return g_last_cuda_error; }
+
+int msda_set_tuning(const char *key, int value)
+{
+    if (key == nullptr) return MSDA_ERR_INVALID_ARGUMENT;
+    const bool ok = (value == 8 || value == 16 || value == 32);
+    if (!strcmp(key, "pairs_d48") && ok) { msda::g_pairs_d48 = value; return MSDA_OK; }
+    if (!strcmp(key, "snip_pairs_d48") && ok) { msda::g_snip_pairs_d48 = value; return MSDA_OK; }
+    return MSDA_ERR_INVALID_ARGUMENT;
+}
 
 const char *msda_error_string(int status)
 {

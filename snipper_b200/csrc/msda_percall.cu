@@ -26,15 +26,31 @@ namespace msda {
 // ------------------------------------------------------------------------------------------
 // FAST fp32 path
 // ------------------------------------------------------------------------------------------
-template <int LANES>
+// A CTA owns a TILE: PAIRS consecutive queries of ONE head of one batch item.  Consecutive
+// queries are neighbouring pixels in the encoder, so the cells they gather overlap and are served
+// from L1 (the first version mapped a CTA to 2 queries x 8 heads: 9 % L1 hit rate, bound by the
+// L2->L1 fill path; see profiles/r01_run1_*).  blockIdx -> (n, query tile, m) with m fastest.
+template <int LANES, int PAIRS_>
 struct FastCfg {
-    static constexpr int kPairsRaw = (256 / LANES) / 8 * 8;
-    static constexpr int PAIRS = kPairsRaw < 8 ? 8 : kPairsRaw;
+    static constexpr int PAIRS = PAIRS_;
     static constexpr int THREADS = PAIRS * LANES;
     static constexpr int SUBS = LANES / 4;                              // 4-lane shuffle groups
     static constexpr int CHUNK = (512 / PAIRS) < 32 ? (512 / PAIRS) : 32;  // samples per pair per pass
-    static_assert(LANES % 4 == 0 && THREADS % 32 == 0, "lane groups must tile warps");
+    static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
+
+struct TileCoord { int n, q0, m; };
+
+__device__ __forceinline__ TileCoord tile_of_block(int M, int Lq, int pairs)
+{
+    const int tiles = (Lq + pairs - 1) / pairs;
+    int b = blockIdx.x;
+    TileCoord t;
+    t.m = b % M; b /= M;
+    t.q0 = (b % tiles) * pairs;
+    t.n = b / tiles;
+    return t;
+}
 
 struct __align__(16) FwdRec {
     int4 off;   // float4-index offsets of the four cells relative to (batch base + m*D), or -1
@@ -47,22 +63,22 @@ struct __align__(16) BwdRec {
     int level;
 };
 
-template <int LANES>
-__global__ void __launch_bounds__(FastCfg<LANES>::THREADS)
+template <int LANES, int PAIRS>
+__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                      const float *__restrict__ attn, float *__restrict__ out,
-                     int M, int L, int P, int LqM, int total_pairs, int64_t value_batch_stride,
+                     int M, int L, int P, int Lq, int64_t value_batch_stride,
                      int cl /* samples per pair per pass */)
 {
-    using Cfg = FastCfg<LANES>;
+    using Cfg = FastCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdRec *rec = reinterpret_cast<FwdRec *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int LP = L * P;
-    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const TileCoord tc = tile_of_block(M, Lq, Cfg::PAIRS);
     const int cell_stride = M * LANES;  // float4 units between consecutive cells
 
     load_level_table(lv, shapes, lsi, L);
@@ -70,14 +86,10 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
 
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
-    const int pair = pair0 + pl;
-    const bool live = pair < total_pairs;
-    const float4 *vbase = nullptr;
-    if (live) {
-        const int b = pair / LqM;
-        const int m = pair % M;
-        vbase = reinterpret_cast<const float4 *>(value + (int64_t)b * value_batch_stride) + m * LANES + lane;
-    }
+    const bool live = tc.q0 + pl < Lq;
+    const size_t pair = ((size_t)tc.n * Lq + tc.q0 + pl) * M + tc.m;
+    const float4 *vbase =
+        reinterpret_cast<const float4 *>(value + (int64_t)tc.n * value_batch_stride) + tc.m * LANES + lane;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int lp0 = 0; lp0 < LP; lp0 += cl) {
@@ -86,12 +98,11 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = i / n;
             const int lp = lp0 + (i - spl * n);
-            const int sp = pair0 + spl;
             FwdRec r;
             r.off = make_int4(-1, -1, -1, -1);
             r.w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (sp < total_pairs) {
-                const size_t si = (size_t)sp * LP + lp;
+            if (tc.q0 + spl < Lq) {
+                const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
                 const float a = __ldg(attn + si);
                 const int l = lp / P;
@@ -130,20 +141,20 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
         }
         if (lp0 + cl < LP) __syncthreads();  // records are reused by the next pass
     }
-    if (live) reinterpret_cast<float4 *>(out)[(size_t)pair * LANES + lane] = acc;
+    if (live) reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(FastCfg<LANES>::THREADS)
+template <int LANES, int PAIRS>
+__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                      const float *__restrict__ attn, const float *__restrict__ grad_out,
                      float *__restrict__ grad_value, float *__restrict__ grad_loc,
                      float *__restrict__ grad_attn,
-                     int S, int M, int L, int P, int LqM, int total_pairs,
+                     int S, int M, int L, int P, int Lq,
                      int64_t value_batch_stride, int cl)
 {
-    using Cfg = FastCfg<LANES>;
+    using Cfg = FastCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdRec *rec = reinterpret_cast<BwdRec *>(smem_raw);
@@ -151,7 +162,7 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
 
     const int tid = threadIdx.x;
     const int LP = L * P;
-    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const TileCoord tc = tile_of_block(M, Lq, Cfg::PAIRS);
     const int cell_stride = M * LANES;
 
     load_level_table(lv, shapes, lsi, L);
@@ -160,18 +171,14 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
     const int sub = lane >> 2;
-    const int pair = pair0 + pl;
-    const bool live = pair < total_pairs;
-    const float4 *vbase = reinterpret_cast<const float4 *>(value);
-    float4 *gvbase = reinterpret_cast<float4 *>(grad_value);
+    const bool live = tc.q0 + pl < Lq;
+    const size_t pair = ((size_t)tc.n * Lq + tc.q0 + pl) * M + tc.m;
+    const float4 *vbase =
+        reinterpret_cast<const float4 *>(value + (int64_t)tc.n * value_batch_stride) + tc.m * LANES + lane;
+    float4 *gvbase =
+        reinterpret_cast<float4 *>(grad_value + (int64_t)tc.n * S * M * (LANES * 4)) + tc.m * LANES + lane;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        const int b = pair / LqM;
-        const int m = pair % M;
-        vbase = reinterpret_cast<const float4 *>(value + (int64_t)b * value_batch_stride) + m * LANES + lane;
-        gvbase = reinterpret_cast<float4 *>(grad_value + (int64_t)b * S * M * (LANES * 4)) + m * LANES + lane;
-        g = ldg4(reinterpret_cast<const float4 *>(grad_out) + (size_t)pair * LANES + lane);
-    }
+    if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
 
     for (int lp0 = 0; lp0 < LP; lp0 += cl) {
         const int n = min(cl, LP - lp0);
@@ -179,12 +186,11 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = i / n;
             const int lp = lp0 + (i - spl * n);
-            const int sp = pair0 + spl;
             BwdRec r;
             r.off = make_int4(-1, -1, -1, -1);
             r.lx = 0.f; r.ly = 0.f; r.a = 0.f; r.level = 0;
-            if (sp < total_pairs) {
-                const size_t si = (size_t)sp * LP + lp;
+            if (tc.q0 + spl < Lq) {
+                const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
                 const int l = lp / P;
                 const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
@@ -250,14 +256,13 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = i / n;
             const int lp = lp0 + (i - spl * n);
-            const int sp = pair0 + spl;
-            if (sp < total_pairs) {
+            if (tc.q0 + spl < Lq) {
                 const float *p = part + (size_t)i * (Cfg::SUBS * 3);
                 float pa = 0.f, px = 0.f, py = 0.f;
 #pragma unroll
                 for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
                 const BwdRec r = rec[i];
-                const size_t si = (size_t)sp * LP + lp;
+                const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
                 grad_attn[si] = pa;
                 reinterpret_cast<float2 *>(grad_loc)[si] =
                     make_float2((float)lv.W[r.level] * r.a * px, (float)lv.H[r.level] * r.a * py);
@@ -278,52 +283,54 @@ bool fast_path_ok(const OpDims &d)
     return true;
 }
 
-template <int LANES>
+int g_pairs_d48 = 16;  // tile length for LANES == 12 (msda_set_tuning("pairs_d48", 8|16|32))
+
+template <int LANES, int PAIRS>
 static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *loc, const float *attn, float *out,
                                    const OpDims &d, cudaStream_t stream)
 {
-    using Cfg = FastCfg<LANES>;
-    const int total_pairs = d.N * d.Lq * d.M;
+    using Cfg = FastCfg<LANES, PAIRS>;
     const int LP = d.L * d.P;
     const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
-    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    const int grid = d.N * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
     const size_t smem = sizeof(FwdRec) * Cfg::PAIRS * cl;
-    msda_fwd_fast_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(
-        value, shapes, lsi, loc, attn, out, d.M, d.L, d.P, d.Lq * d.M, total_pairs,
-        d.value_batch_stride, cl);
+    msda_fwd_fast_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
+        value, shapes, lsi, loc, attn, out, d.M, d.L, d.P, d.Lq, d.value_batch_stride, cl);
     return cudaGetLastError();
 }
 
-template <int LANES>
+template <int LANES, int PAIRS>
 static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *loc, const float *attn, const float *grad_out,
                                    float *grad_value, float *grad_loc, float *grad_attn,
                                    const OpDims &d, cudaStream_t stream)
 {
-    using Cfg = FastCfg<LANES>;
-    const int total_pairs = d.N * d.Lq * d.M;
+    using Cfg = FastCfg<LANES, PAIRS>;
     const int LP = d.L * d.P;
     const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
-    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    const int grid = d.N * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
     const size_t smem = (sizeof(BwdRec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * cl;
-    msda_bwd_fast_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(
+    msda_bwd_fast_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
         value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d.S, d.M, d.L,
-        d.P, d.Lq * d.M, total_pairs, d.value_batch_stride, cl);
+        d.P, d.Lq, d.value_batch_stride, cl);
     return cudaGetLastError();
 }
 
-#define MSDA_DISPATCH_LANES(D, CALL)                 \
-    switch ((D) / 4) {                               \
-        case 4: return CALL(4);                      \
-        case 8: return CALL(8);                      \
-        case 12: return CALL(12);                    \
-        case 16: return CALL(16);                    \
-        case 20: return CALL(20);                    \
-        case 24: return CALL(24);                    \
-        case 28: return CALL(28);                    \
-        case 32: return CALL(32);                    \
-        default: return cudaErrorInvalidValue;       \
+#define MSDA_DISPATCH_LANES(D, CALL)                                  \
+    switch ((D) / 4) {                                                \
+        case 4: return CALL(4, 16);                                   \
+        case 8: return CALL(8, 16);                                   \
+        case 12:                                                      \
+            if (g_pairs_d48 == 8) return CALL(12, 8);                 \
+            if (g_pairs_d48 == 32) return CALL(12, 32);               \
+            return CALL(12, 16);                                      \
+        case 16: return CALL(16, 16);                                 \
+        case 20: return CALL(20, 16);                                 \
+        case 24: return CALL(24, 16);                                 \
+        case 28: return CALL(28, 16);                                 \
+        case 32: return CALL(32, 16);                                 \
+        default: return cudaErrorInvalidValue;                        \
     }
 
 cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
@@ -331,7 +338,7 @@ cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, c
                                     const OpDims &d, cudaStream_t stream)
 {
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
-#define CALL(LN) launch_fwd_fast<LN>(value, shapes, lsi, loc, attn, out, d, stream)
+#define CALL(LN, PR) launch_fwd_fast<LN, PR>(value, shapes, lsi, loc, attn, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }
@@ -342,8 +349,8 @@ cudaError_t launch_backward_fast_f32(const float *value, const int64_t *shapes, 
                                      const OpDims &d, cudaStream_t stream)
 {
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
-#define CALL(LN) \
-    launch_bwd_fast<LN>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d, stream)
+#define CALL(LN, PR) \
+    launch_bwd_fast<LN, PR>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }

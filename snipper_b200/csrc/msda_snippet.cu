@@ -22,13 +22,29 @@ namespace msda {
 
 constexpr int kSnippetMaxLP = 32;
 
-template <int LANES>
+// A CTA owns PAIRS consecutive queries of ONE head of one (batch item, query frame): neighbouring
+// encoder queries gather overlapping cells, which then hit in L1 (see msda_percall.cu).
+template <int LANES, int PAIRS_>
 struct SnipCfg {
-    static constexpr int PAIRS = LANES <= 16 ? 16 : 8;
+    static constexpr int PAIRS = PAIRS_;
     static constexpr int THREADS = PAIRS * LANES;
     static constexpr int SUBS = LANES / 4;
-    static_assert(LANES % 4 == 0 && THREADS % 32 == 0, "lane groups must tile warps");
+    static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
+
+struct SnipTile { int n, t1, q0, m; };
+
+__device__ __forceinline__ SnipTile snippet_tile_of_block(int M, int Lq, int T1, int pairs)
+{
+    const int tiles = (Lq + pairs - 1) / pairs;
+    int b = blockIdx.x;
+    SnipTile t;
+    t.m = b % M; b /= M;
+    t.q0 = (b % tiles) * pairs; b /= tiles;
+    t.t1 = b % T1;
+    t.n = b / T1;
+    return t;
+}
 
 struct __align__(16) SnipFwdRec {
     int4 off;
@@ -58,34 +74,26 @@ __device__ __forceinline__ float pair_softmax(const float *__restrict__ z, int L
     return expf(__ldg(z + lp) - mx) / sum * inv_k;
 }
 
-struct PairCoord { int n, t1, q, m; };
-
-__device__ __forceinline__ PairCoord split_pair(int pair, int M, int Lq, int T1)
-{
-    PairCoord c;
-    c.m = pair % M; pair /= M;
-    c.q = pair % Lq; pair /= Lq;
-    c.t1 = pair % T1;
-    c.n = pair / T1;
-    return c;
-}
-
-template <int LANES>
-__global__ void __launch_bounds__(SnipCfg<LANES>::THREADS)
+template <int LANES, int PAIRS>
+__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS)
 msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
-                        float *__restrict__ out, SnippetDims d, int total_pairs)
+                        float *__restrict__ out, SnippetDims d)
 {
-    using Cfg = SnipCfg<LANES>;
+    using Cfg = SnipCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SnipFwdRec *rec = reinterpret_cast<SnipFwdRec *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int LP = d.L * d.P;
-    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const SnipTile tc = snippet_tile_of_block(d.M, d.Lq, d.T1, Cfg::PAIRS);
     const int cell_stride = d.M * LANES;
+    int lo, hi;
+    frame_range(tc.t1, d.n_frame, d.T2, lo, hi);
+    const int nf = hi - lo + 1;
+    const size_t qbase = ((size_t)tc.n * d.T1 + tc.t1) * d.Lq;  // first query row of this (n, t1)
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
@@ -94,18 +102,16 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
     for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
         const int spl = i / LP;
         const int lp = i - spl * LP;
-        const int sp = pair0 + spl;
+        const int q = tc.q0 + spl;
         SnipFwdRec r;
         r.off = make_int4(-1, -1, -1, -1);
         r.w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sp < total_pairs) {
-            const PairCoord c = split_pair(sp, d.M, d.Lq, d.T1);
-            int lo, hi;
-            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
-            const float a = pair_softmax(logits + (size_t)sp * LP, LP, lp, 1.f / (float)(hi - lo + 1));
+        if (q < d.Lq) {
+            const size_t sp = (qbase + q) * d.M + tc.m;
+            const float a = pair_softmax(logits + sp * LP, LP, lp, 1.f / (float)nf);
             const int l = lp / d.P;
-            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + (size_t)sp * LP + lp);
-            const float *rp = ref + c.n * d.ref_stride_n + c.t1 * d.ref_stride_t + ((int64_t)c.q * d.L + l) * 2;
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
+            const float *rp = ref + tc.n * d.ref_stride_n + tc.t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
             const float u = __ldg(rp) + o.x / (float)lv.W[l];
             const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
             const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
@@ -123,15 +129,11 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
     // ---- phase 2: gather from every neighbour frame ----
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
-    const int pair = pair0 + pl;
-    if (pair >= total_pairs) return;
-    const PairCoord c = split_pair(pair, d.M, d.Lq, d.T1);
-    int lo, hi;
-    frame_range(c.t1, d.n_frame, d.T2, lo, hi);
-    const float4 *vframe = reinterpret_cast<const float4 *>(value + c.n * d.value_stride_n + lo * d.value_stride_t) +
-                           c.m * LANES + lane;
+    if (tc.q0 + pl >= d.Lq) return;
+    const size_t pair = (qbase + tc.q0 + pl) * d.M + tc.m;
+    const float4 *vframe = reinterpret_cast<const float4 *>(value + tc.n * d.value_stride_n + lo * d.value_stride_t) +
+                           tc.m * LANES + lane;
     const int64_t fstride = d.value_stride_t / 4;  // float4 units
-    const int nf = hi - lo + 1;
     const SnipFwdRec *my = rec + pl * LP;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
@@ -155,19 +157,19 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
             acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
         }
     }
-    reinterpret_cast<float4 *>(out)[(size_t)pair * LANES + lane] = acc;
+    reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(SnipCfg<LANES>::THREADS)
+template <int LANES, int PAIRS>
+__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS)
 msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
                         const float *__restrict__ grad_out, float *__restrict__ grad_value,
                         float *__restrict__ grad_offsets, float *__restrict__ grad_logits,
-                        SnippetDims d, int total_pairs)
+                        SnippetDims d)
 {
-    using Cfg = SnipCfg<LANES>;
+    using Cfg = SnipCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SnipBwdRec *rec = reinterpret_cast<SnipBwdRec *>(smem_raw);
@@ -175,8 +177,12 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     float *part = reinterpret_cast<float *>(smem_raw + sizeof(SnipBwdRec) * Cfg::PAIRS * LP);  // [rec][SUBS][3]
 
     const int tid = threadIdx.x;
-    const int pair0 = blockIdx.x * Cfg::PAIRS;
+    const SnipTile tc = snippet_tile_of_block(d.M, d.Lq, d.T1, Cfg::PAIRS);
     const int cell_stride = d.M * LANES;
+    int lo, hi;
+    frame_range(tc.t1, d.n_frame, d.T2, lo, hi);
+    const int nf = hi - lo + 1;
+    const size_t qbase = ((size_t)tc.n * d.T1 + tc.t1) * d.Lq;
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
@@ -185,17 +191,15 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
         const int spl = i / LP;
         const int lp = i - spl * LP;
-        const int sp = pair0 + spl;
+        const int q = tc.q0 + spl;
         SnipBwdRec r;
         r.off = make_int4(-1, -1, -1, -1);
         r.lx = 0.f; r.ly = 0.f; r.a = 0.f; r.level = 0;
-        if (sp < total_pairs) {
-            const PairCoord c = split_pair(sp, d.M, d.Lq, d.T1);
-            int lo, hi;
-            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+        if (q < d.Lq) {
+            const size_t sp = (qbase + q) * d.M + tc.m;
             const int l = lp / d.P;
-            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + (size_t)sp * LP + lp);
-            const float *rp = ref + c.n * d.ref_stride_n + c.t1 * d.ref_stride_t + ((int64_t)c.q * d.L + l) * 2;
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
+            const float *rp = ref + tc.n * d.ref_stride_n + tc.t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
             const float u = __ldg(rp) + o.x / (float)lv.W[l];
             const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
             const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
@@ -204,7 +208,7 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
             r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
             r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
             r.lx = s.lx; r.ly = s.ly; r.level = l;
-            r.a = pair_softmax(logits + (size_t)sp * LP, LP, lp, 1.f / (float)(hi - lo + 1));
+            r.a = pair_softmax(logits + sp * LP, LP, lp, 1.f / (float)nf);
         }
         rec[i] = r;
     }
@@ -215,23 +219,16 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
         const int pl = tid / LANES;
         const int lane = tid - pl * LANES;
         const int sub = lane >> 2;
-        const int pair = pair0 + pl;
-        const bool live = pair < total_pairs;
-        const float4 *vframe = reinterpret_cast<const float4 *>(value);
-        float4 *gvframe = reinterpret_cast<float4 *>(grad_value);
+        const bool live = tc.q0 + pl < d.Lq;
+        const size_t pair = (qbase + tc.q0 + pl) * d.M + tc.m;
+        const float4 *vframe =
+            reinterpret_cast<const float4 *>(value + tc.n * d.value_stride_n + lo * d.value_stride_t) +
+            tc.m * LANES + lane;
+        float4 *gvframe =
+            reinterpret_cast<float4 *>(grad_value + ((int64_t)tc.n * d.T2 + lo) * d.S * d.M * (LANES * 4)) +
+            tc.m * LANES + lane;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        int nf = 0;
-        if (live) {
-            const PairCoord c = split_pair(pair, d.M, d.Lq, d.T1);
-            int lo, hi;
-            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
-            nf = hi - lo + 1;
-            vframe = reinterpret_cast<const float4 *>(value + c.n * d.value_stride_n + lo * d.value_stride_t) +
-                     c.m * LANES + lane;
-            gvframe = reinterpret_cast<float4 *>(grad_value + ((int64_t)c.n * d.T2 + lo) * d.S * d.M * (LANES * 4)) +
-                      c.m * LANES + lane;
-            g = ldg4(reinterpret_cast<const float4 *>(grad_out) + (size_t)pair * LANES + lane);
-        }
+        if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
         const int64_t fstride = d.value_stride_t / 4;
         const int64_t gfstride = (int64_t)d.S * d.M * LANES;
         const SnipBwdRec *my = rec + pl * LP;
@@ -295,11 +292,12 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
         for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
         pa_i[it] = pa;
         const SnipBwdRec r = rec[i];
-        const int sp = pair0 + i / LP;
-        if (sp < total_pairs) {
+        const int spl = i / LP;
+        if (tc.q0 + spl < d.Lq) {
             // loc = ref + off/(W,H) and x = loc*W - 0.5  =>  dx/doff_x = 1: the W factor of the
             // per-call grad_loc (W*A*px) cancels against the 1/W of the normalisation.
-            reinterpret_cast<float2 *>(grad_offsets)[(size_t)pair0 * LP + i] = make_float2(r.a * px, r.a * py);
+            const size_t si = ((qbase + tc.q0 + spl) * d.M + tc.m) * LP + (i - spl * LP);
+            reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(r.a * px, r.a * py);
         }
         part[(size_t)i * (Cfg::SUBS * 3)] = pa * r.a;  // own slot only
     }
@@ -307,14 +305,11 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     it = 0;
     for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS, ++it) {
         const int spl = i / LP;
-        const int sp = pair0 + spl;
-        if (sp < total_pairs) {
-            const PairCoord c = split_pair(sp, d.M, d.Lq, d.T1);
-            int lo, hi;
-            frame_range(c.t1, d.n_frame, d.T2, lo, hi);
+        if (tc.q0 + spl < d.Lq) {
             float dot = 0.f;
             for (int j = 0; j < LP; ++j) dot += part[(size_t)(spl * LP + j) * (Cfg::SUBS * 3)];
-            grad_logits[(size_t)pair0 * LP + i] = rec[i].a * (pa_i[it] - (float)(hi - lo + 1) * dot);
+            const size_t si = ((qbase + tc.q0 + spl) * d.M + tc.m) * LP + (i - spl * LP);
+            grad_logits[si] = rec[i].a * (pa_i[it] - (float)nf * dot);
         }
     }
 }
@@ -329,46 +324,51 @@ bool snippet_ok(const SnippetDims &d)
     return true;
 }
 
-template <int LANES>
+int g_snip_pairs_d48 = 16;  // msda_set_tuning("snip_pairs_d48", 8|16|32)
+
+template <int LANES, int PAIRS>
 static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *offsets, const float *logits, const float *ref,
                                    float *out, const SnippetDims &d, cudaStream_t stream)
 {
-    using Cfg = SnipCfg<LANES>;
-    const int total_pairs = d.N * d.T1 * d.Lq * d.M;
-    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    using Cfg = SnipCfg<LANES, PAIRS>;
+    const int grid = d.N * d.T1 * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
     const size_t smem = sizeof(SnipFwdRec) * Cfg::PAIRS * d.L * d.P;
-    msda_snippet_fwd_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets, logits,
-                                                                        ref, out, d, total_pairs);
+    msda_snippet_fwd_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets,
+                                                                               logits, ref, out, d);
     return cudaGetLastError();
 }
 
-template <int LANES>
+template <int LANES, int PAIRS>
 static cudaError_t launch_snip_bwd(const float *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *offsets, const float *logits, const float *ref,
                                    const float *grad_out, float *grad_value, float *grad_offsets,
                                    float *grad_logits, const SnippetDims &d, cudaStream_t stream)
 {
-    using Cfg = SnipCfg<LANES>;
-    const int total_pairs = d.N * d.T1 * d.Lq * d.M;
-    const int grid = (total_pairs + Cfg::PAIRS - 1) / Cfg::PAIRS;
+    using Cfg = SnipCfg<LANES, PAIRS>;
+    const int grid = d.N * d.T1 * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
     const size_t smem = (sizeof(SnipBwdRec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
-    msda_snippet_bwd_kernel<LANES><<<grid, Cfg::THREADS, smem, stream>>>(
-        value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, total_pairs);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(msda_snippet_bwd_kernel<LANES, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    msda_snippet_bwd_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
+        value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d);
     return cudaGetLastError();
 }
 
-#define MSDA_DISPATCH_LANES(D, CALL)                 \
-    switch ((D) / 4) {                               \
-        case 4: return CALL(4);                      \
-        case 8: return CALL(8);                      \
-        case 12: return CALL(12);                    \
-        case 16: return CALL(16);                    \
-        case 20: return CALL(20);                    \
-        case 24: return CALL(24);                    \
-        case 28: return CALL(28);                    \
-        case 32: return CALL(32);                    \
-        default: return cudaErrorInvalidValue;       \
+#define MSDA_DISPATCH_LANES(D, CALL)                                  \
+    switch ((D) / 4) {                                                \
+        case 4: return CALL(4, 16);                                   \
+        case 8: return CALL(8, 16);                                   \
+        case 12:                                                      \
+            if (g_snip_pairs_d48 == 8) return CALL(12, 8);            \
+            if (g_snip_pairs_d48 == 32) return CALL(12, 32);          \
+            return CALL(12, 16);                                      \
+        case 16: return CALL(16, 16);                                 \
+        case 20: return CALL(20, 8);                                  \
+        case 24: return CALL(24, 8);                                  \
+        case 28: return CALL(28, 8);                                  \
+        case 32: return CALL(32, 8);                                  \
+        default: return cudaErrorInvalidValue;                        \
     }
 
 cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes,
@@ -376,7 +376,7 @@ cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes
                                        const float *logits, const float *ref, float *out,
                                        const SnippetDims &d, cudaStream_t stream)
 {
-#define CALL(LN) launch_snip_fwd<LN>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
+#define CALL(LN, PR) launch_snip_fwd<LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }
@@ -388,8 +388,8 @@ cudaError_t launch_snippet_backward_f32(const float *value, const int64_t *shape
                                         float *grad_offsets, float *grad_logits,
                                         const SnippetDims &d, cudaStream_t stream)
 {
-#define CALL(LN) \
-    launch_snip_bwd<LN>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
+#define CALL(LN, PR) \
+    launch_snip_bwd<LN, PR>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }

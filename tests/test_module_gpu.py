@@ -1,0 +1,157 @@
+"""GPU parity tests of the ``MSDeformAttn`` module (fused snippet kernels and per-call loop)
+against (a) golden vectors from the reference module and (b) the CPU oracle restatement."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import level_start_index, load_golden, rel_err
+from oracle import torch_ref
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _golden_module(g, mode, dtype):
+    from snipper_b200 import MSDeformAttn
+    d_model, L, M, P, n_frame, T1, T2, Lq, N = [int(x) for x in g["cfg"]]
+    mod = MSDeformAttn(d_model, L, M, P, n_frame, mode, False, mode == "decoder")
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd.")}
+    mod.load_state_dict(sd, strict=True)  # reference checkpoint keys load as-is
+    return mod.to(DEV, dtype)
+
+
+@pytest.mark.parametrize("mode", ["encoder", "decoder"])
+@pytest.mark.parametrize("dtype,ftol,btol", [(torch.float64, 1e-10, 1e-9), (torch.float32, 1e-5, 1e-4)])
+def test_module_golden(mode, dtype, ftol, btol):
+    """Reference MSDeformAttn (use_pytroch_deform=True, fp64) vs ours; D=12 -> per-call path."""
+    g = load_golden("module_" + mode)
+    mod = _golden_module(g, mode, dtype)
+    d_model = int(g["cfg"][0])
+    query = T(g["query"]).to(DEV, dtype).requires_grad_(True)
+    ref = T(g["ref"]).to(DEV, dtype).requires_grad_(True)
+    src = T(g["src"]).to(DEV, dtype).requires_grad_(True)
+    mask = T(g["mask"])[..., None].expand(-1, -1, -1, d_model).to(DEV)
+    res = mod(query, ref, src, T(g["shapes"]).to(DEV), T(g["lsi"]).to(DEV), mask)
+    out, vis = res if mode == "decoder" else (res, None)
+    assert rel_err(out, g["out"]) < ftol
+    out.backward(T(g["grad_out"]).to(DEV, dtype))
+    assert rel_err(query.grad, g["grad_query"]) < btol
+    assert rel_err(ref.grad, g["grad_ref"]) < btol
+    assert rel_err(src.grad, g["grad_src"]) < btol
+    for k, p in mod.named_parameters():
+        assert rel_err(p.grad, g["pg." + k]) < btol, k
+    if vis is not None:
+        for t1, (vl, va) in enumerate(zip(*vis)):
+            assert rel_err(vl, g["vis_loc.%d" % t1]) < ftol
+            assert rel_err(va, g["vis_att.%d" % t1]) < ftol
+
+
+def _pair(d_model, M, L, P, n_frame, mode, seed):
+    """(ours on GPU fp32, oracle restatement on CPU fp64) with identical perturbed weights."""
+    from snipper_b200 import MSDeformAttn
+    torch.manual_seed(seed)
+    vis = mode == "decoder"
+    ours = MSDeformAttn(d_model, L, M, P, n_frame, mode, False, vis)
+    with torch.no_grad():
+        ours.sampling_offsets[0].weight.normal_(0, 0.2)
+        ours.attention_weights[0].weight.normal_(0, 0.3)
+        ours.attention_weights[0].bias.normal_(0, 0.3)
+    oracle = torch_ref.SnippetMSDeformAttnRef(d_model, L, M, P, n_frame, mode, True, vis).double()
+    oracle.load_state_dict({k: v.double() for k, v in ours.state_dict().items()})
+    return ours.to(DEV), oracle
+
+
+def _inputs(N, T1, T2, Lq, shapes, d_model, seed, encoder_ref=False):
+    g = torch.Generator().manual_seed(seed)
+    L = shapes.shape[0]
+    S = int(shapes.prod(1).sum())
+    query = torch.randn(N, T1, Lq, d_model, generator=g)
+    src = torch.randn(N, T2, S, d_model, generator=g)
+    if encoder_ref:  # one frame of reference points expanded over T1 (stride 0), as the encoder does
+        ref = torch.rand(N, 1, Lq, L, 2, generator=g).expand(N, T1, Lq, L, 2)
+    else:
+        ref = torch.rand(N, T1, Lq, L, 2, generator=g)
+    mask = (torch.rand(N, 1, S, 1, generator=g) < 0.1).expand(N, T2, S, d_model)
+    grad_out = torch.randn(N, T1, Lq, d_model, generator=g)
+    return query, ref, src, mask, grad_out
+
+
+def _run(mod, dev, dtype, query, ref, src, mask, grad_out, shapes):
+    q = query.to(dev, dtype).requires_grad_(True)
+    r = ref.to(dev, dtype).requires_grad_(True)
+    s = src.to(dev, dtype).requires_grad_(True)
+    for p in mod.parameters():
+        p.grad = None
+    res = mod(q, r, s, shapes.to(dev), level_start_index(shapes).to(dev), mask.to(dev))
+    out, vis = res if isinstance(res, tuple) else (res, None)
+    out.backward(grad_out.to(dev, dtype))
+    pg = {k: p.grad.detach().cpu() for k, p in mod.named_parameters()}
+    return out.detach().cpu(), q.grad.cpu(), r.grad.cpu(), s.grad.cpu(), pg, vis
+
+
+CONFIGS = [
+    # d_model, M, L, P, n_frame, mode, T1 extra (future frames), Lq (None = S)
+    (128, 8, 3, 4, 4, "encoder", 0, None),
+    (128, 8, 3, 4, 4, "decoder", 2, 7),
+    (384, 8, 3, 4, 4, "encoder", 0, None),   # Snipper: D = 48
+    (384, 8, 3, 4, 4, "decoder", 2, 60),
+    (384, 8, 3, 4, 1, "encoder", 0, None),   # T = 1 (BASELINE config 1)
+    (256, 4, 2, 8, 3, "decoder", 1, 5),      # D = 64, P = 8
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_fused_module_vs_oracle(cfg):
+    d_model, M, L, P, n_frame, mode, fut, Lq = cfg
+    shapes = torch.as_tensor([(9, 12), (5, 6), (3, 3)][:L], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    ours, oracle = _pair(d_model, M, L, P, n_frame, mode, seed=7)
+    assert ours._can_fuse(torch.empty(1, device=DEV))
+    N, T1, T2 = 2, n_frame + fut, n_frame
+    inp = _inputs(N, T1, T2, Lq or S, shapes, d_model, seed=8, encoder_ref=(mode == "encoder"))
+    got = _run(ours, DEV, torch.float32, *inp, shapes)
+    want = _run(oracle, "cpu", torch.float64, *inp, shapes)
+    assert rel_err(got[0], want[0]) < 1e-5
+    for i in (1, 2, 3):
+        assert rel_err(got[i], want[i]) < 1e-4, i
+    for k in want[4]:
+        assert rel_err(got[4][k], want[4][k]) < 1e-4, k
+    if mode == "decoder":
+        for a, b in zip(got[5][0], want[5][0]):
+            assert a.shape == b.shape and rel_err(a, b) < 1e-5
+        for a, b in zip(got[5][1], want[5][1]):
+            assert a.shape == b.shape and rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("mode,fut,Lq", [("encoder", 0, None), ("decoder", 2, 11)])
+def test_fused_equals_per_call_loop(mode, fut, Lq):
+    """The one-launch fused path and the reference-style (t1,t2) loop agree on the GPU."""
+    shapes = torch.as_tensor([(9, 12), (5, 6), (3, 3)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    ours, _ = _pair(384, 8, 3, 4, 4, mode, seed=3)
+    loop = copy.deepcopy(ours)
+    loop.fused = False
+    inp = _inputs(2, 4 + fut, 4, Lq or S, shapes, 384, seed=4)
+    a = _run(ours, DEV, torch.float32, *inp, shapes)
+    b = _run(loop, DEV, torch.float32, *inp, shapes)
+    assert rel_err(a[0], b[0]) < 1e-5
+    for i in (1, 2, 3):
+        assert rel_err(a[i], b[i]) < 1e-4
+    for k in b[4]:
+        assert rel_err(a[4][k], b[4][k]) < 1e-4, k
+
+
+def test_unaliased_slots_fall_back_to_loop():
+    """If a user un-aliases the frame slots, the fused shortcut is invalid and must not be taken."""
+    from snipper_b200 import MSDeformAttn
+    mod = MSDeformAttn(128, 3, 8, 4, 4, "encoder").to(DEV)
+    assert mod._can_fuse(torch.empty(1, device=DEV))
+    mod.sampling_offsets[1] = copy.deepcopy(mod.sampling_offsets[0])
+    assert not mod._can_fuse(torch.empty(1, device=DEV))

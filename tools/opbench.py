@@ -38,6 +38,21 @@ def make(N, Lq, M=8, D=48, P=4, levels=LEVELS, regime="local", device="cuda", se
     value = torch.randn(N, S, M, D, generator=g)
     if regime == "uniform" or Lq != S:
         loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+    elif regime == "init":
+        # what a randomly initialised Snipper produces: pixel centres + a fixed per-head direction
+        # times (p+1) px (reference ms_deform_attn.py:82-87) -- best-case locality
+        import math
+        refs = []
+        for H, W in levels:
+            ys, xs = torch.meshgrid(torch.arange(H) + 0.5, torch.arange(W) + 0.5, indexing="ij")
+            refs.append(torch.stack([xs.reshape(-1) / W, ys.reshape(-1) / H], -1))
+        ref = torch.cat(refs, 0)
+        th = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        d = torch.stack([th.cos(), th.sin()], -1)
+        d = d / d.abs().max(-1, keepdim=True)[0]
+        off = d.view(1, 1, M, 1, 1, 2) * torch.arange(1, P + 1, dtype=torch.float32).view(1, 1, 1, 1, P, 1)
+        wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
+        loc = (ref[None, :, None, None, None, :] + off / wh[None, None, None, :, None, :]).expand(N, Lq, M, L, P, 2).contiguous()
     else:  # encoder-like: pixel centres + N(0, 3px)
         refs = []
         for H, W in levels:
@@ -52,23 +67,125 @@ def make(N, Lq, M=8, D=48, P=4, levels=LEVELS, regime="local", device="cuda", se
     return [t.to(device) for t in (value, shapes, lsi, loc, attn, go)]
 
 
-def time_fn(fn, iters, flush):
+WARMUP = 5
+
+
+def time_fn(fn, iters, flush, inner=10):
+    """Per-launch device time in us.  Without --flush: `inner` back-to-back launches between two
+    events (host launch overhead hidden behind the queue).  With --flush: a 256 MiB memset evicts
+    L2 before every single launch; the memset also keeps the queue busy, hiding host overhead."""
     buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if flush else None
-    for _ in range(5):
+    for _ in range(WARMUP):
         fn()
     torch.cuda.synchronize()
     times = []
     for _ in range(iters):
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
         if buf is not None:
             buf.zero_()
-        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
-        s.record()
-        fn()
-        e.record()
+            s.record()
+            fn()
+            e.record()
+            n = 1
+        else:
+            s.record()
+            for _ in range(inner):
+                fn()
+            e.record()
+            n = inner
         e.synchronize()
-        times.append(s.elapsed_time(e) * 1e3)
+        times.append(s.elapsed_time(e) * 1e3 / n)
     times.sort()
     return times[len(times) // 2], times[0]
+
+
+def direct_calls(value, shapes, lsi, loc, attn, go):
+    """Forward/backward closures that call the C ABI directly (ctypes), bypassing the torch
+    custom-op dispatcher (~30 us of host time per call, which would hide a 20 us kernel)."""
+    from snipper_b200 import capi
+    L = capi.lib()
+    N, S, M, D = value.shape
+    _, Lq, _, Lv, P, _ = loc.shape
+    out = torch.empty(N, Lq, M * D, device=value.device)
+    gv, gl, ga = torch.empty_like(value), torch.empty_like(loc), torch.empty_like(attn)
+    st = torch.cuda.current_stream().cuda_stream
+    keep = (out, gv, gl, ga)
+
+    def fwd():
+        r = L.msda_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                           out.data_ptr(), N, S, M, D, Lv, Lq, P, 0, 64, 0, st)
+        assert r == 0, r
+
+    def bwd():
+        r = L.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                            go.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), N, S, M, D, Lv, Lq, P,
+                            0, 64, 0, 0, 0, 0, st)
+        assert r == 0, r
+
+    def bwd_nomemset():
+        r = L.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                            go.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), N, S, M, D, Lv, Lq, P,
+                            0, 64, 0, capi.MSDA_FLAG_ACCUMULATE_VALUE, 0, 0, st)
+        assert r == 0, r
+
+    return fwd, bwd, bwd_nomemset, keep
+
+
+def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encoder=True, seed=0, regime="local"):
+    """Closures timing the fused per-layer entry points directly through the C ABI."""
+    from snipper_b200 import capi
+    L = capi.lib()
+    g = torch.Generator().manual_seed(seed)
+    shapes = torch.as_tensor(levels, dtype=torch.long)
+    Lv = len(levels)
+    S = int(shapes.prod(1).sum())
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, T2, S, M, D, generator=g).cuda()
+    if regime == "init":
+        import math
+        th = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        dd = torch.stack([th.cos(), th.sin()], -1)
+        dd = dd / dd.abs().max(-1, keepdim=True)[0]
+        offsets = (dd.view(1, 1, 1, M, 1, 1, 2) * torch.arange(1, P + 1, dtype=torch.float32).view(1, 1, 1, 1, 1, P, 1)
+                   ).expand(N, T1, Lq, M, Lv, P, 2).contiguous().cuda()
+    else:
+        offsets = (torch.randn(N, T1, Lq, M, Lv, P, 2, generator=g) * 3.0).cuda()
+    logits = torch.randn(N, T1, Lq, M, Lv, P, generator=g).cuda()
+    if encoder:
+        refs = []
+        for H, W in levels:
+            ys, xs = torch.meshgrid(torch.arange(H) + 0.5, torch.arange(W) + 0.5, indexing="ij")
+            refs.append(torch.stack([xs.reshape(-1) / W, ys.reshape(-1) / H], -1))
+        ref = torch.cat(refs, 0)[None, None, :, None, :].expand(N, T1, Lq, Lv, 2).contiguous().cuda()
+    else:
+        ref = torch.rand(N, T1, Lq, Lv, 2, generator=g).cuda()
+    go = torch.randn(N, T1, Lq, M * D, generator=g).cuda()
+    out = torch.empty_like(go)
+    gv, goff, glog = torch.empty_like(value), torch.empty_like(offsets), torch.empty_like(logits)
+    shapes, lsi = shapes.cuda(), lsi.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    keep = (value, offsets, logits, ref, go, out, gv, goff, glog, shapes, lsi)
+    rs = (ref.stride(0), ref.stride(1))
+
+    def fwd():
+        r = L.msda_snippet_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                   logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
+                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, st)
+        assert r == 0, r
+
+    def bwd():
+        r = L.msda_snippet_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                    logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(),
+                                    goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
+                                    0, 0, rs[0], rs[1], 0, 0, st)
+        assert r == 0, r
+
+    e = 4
+    samples = N * T1 * Lq * M * Lv * P
+    vbytes = min(N * T2 * S * M * D, 4 * samples * D * 3)
+    fwd_b = e * (vbytes + 3 * samples + N * T1 * Lq * M * D)
+    bwd_b = e * (2 * vbytes + N * T1 * Lq * M * D + 6 * samples)
+    return fwd, bwd, fwd_b, bwd_b, keep
 
 
 def main():
@@ -77,20 +194,44 @@ def main():
     ap.add_argument("--flush", action="store_true")
     ap.add_argument("--ref", action="store_true", help="also time the vendored reference op")
     ap.add_argument("--regime", default="local")
+    ap.add_argument("--pairs", type=int, default=0, help="tile length knob for D=48 (8/16/32)")
+    ap.add_argument("--snip-pairs", type=int, default=0)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--cases", default="snip_enc_N1,snip_dec_N1,enc_N1,enc_N2,enc_N8,dec_N1,dec_N2")
     args = ap.parse_args()
+    global WARMUP
+    WARMUP = args.warmup
     import snipper_b200  # noqa: F401
+    from snipper_b200 import capi
+    if args.pairs:
+        assert capi.lib().msda_set_tuning(b"pairs_d48", args.pairs) == 0
     ref = None
     if args.ref:
         from oracle.build_ref import load_ref
         ref = load_ref()
     S = sum(h * w for h, w in LEVELS)
     cases = [("enc_N1", 1, S), ("enc_N2", 2, S), ("enc_N8", 8, S), ("dec_N1", 1, 60), ("dec_N2", 2, 60)]
+    if args.snip_pairs:
+        assert capi.lib().msda_set_tuning(b"snip_pairs_d48", args.snip_pairs) == 0
+    for name, N, T1, Lq, enc in (("snip_enc_N1", 1, 4, S, True), ("snip_dec_N1", 1, 6, 60, False)):
+        if name not in args.cases.split(","):
+            continue
+        fwd, bwd, fb, bb, keep = snippet_calls(N, T1, 4, Lq, encoder=enc, regime=args.regime)
+        for which, fn, nbytes in (("fwd", fwd, fb), ("bwd", bwd, bb)):
+            med, best = time_fn(fn, args.iters, args.flush)
+            print(json.dumps({"case": name, "impl": "ours_fused_layer", "pass": which, "us_median": round(med, 2),
+                              "us_best": round(best, 2), "alg_MB": round(nbytes / 1e6, 2),
+                              "GBps": round(nbytes / med / 1e3, 1),
+                              "frac_of_measured_hbm": round(nbytes / med / 1e3 / PEAK, 4),
+                              "l2_flush": args.flush, "regime": args.regime, "pairs": args.snip_pairs or 16}))
+        del keep
     for name, N, Lq in cases:
+        if name not in args.cases.split(","):
+            continue
         value, shapes, lsi, loc, attn, go = make(N, Lq, regime=args.regime)
         fb, bb = algorithmic_bytes(N, S, 8, 48, 3, 4, Lq)
-        fwd = lambda: torch.ops.snipper_b200.msda_forward(value, shapes, lsi, loc, attn, 64)
-        bwd = lambda: torch.ops.snipper_b200.msda_backward(value, shapes, lsi, loc, attn, go, 64, False)
-        rows = [("ours", "fwd", fwd, fb), ("ours", "bwd", bwd, bb)]
+        fwd, bwd, bwd_nm, keep = direct_calls(value, shapes, lsi, loc, attn, go)
+        rows = [("ours", "fwd", fwd, fb), ("ours", "bwd", bwd, bb), ("ours", "bwd_nomemset", bwd_nm, bb)]
         if ref is not None:
             rows += [("vendored", "fwd", lambda: ref.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 64), fb),
                      ("vendored", "bwd", lambda: ref.ms_deform_attn_backward(value, shapes, lsi, loc, attn, go, 64), bb)]
@@ -99,7 +240,7 @@ def main():
             print(json.dumps({"case": name, "impl": impl, "pass": which, "us_median": round(med, 2),
                               "us_best": round(best, 2), "alg_MB": round(nbytes / 1e6, 2),
                               "GBps": round(nbytes / med / 1e3, 1), "frac_of_measured_hbm": round(nbytes / med / 1e3 / PEAK, 4),
-                              "l2_flush": args.flush, "regime": args.regime}))
+                              "l2_flush": args.flush, "regime": args.regime, "pairs": args.pairs or 16}))
 
 
 if __name__ == "__main__":
