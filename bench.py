@@ -1,0 +1,335 @@
+"""bench.py -- headline benchmark of the B200-native MSDeformAttn engine for Snipper.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on):
+  Snipper T=4 snippet, 600x800, ResNet-50 -> 3 levels -> hidden 384, 8 heads, enc6/dec6, L=3,
+  P=4, 60 queries x 15 keypoints, inference, batch 1 per GPU, random-init weights, synthetic
+  frames.  A "step" is one snippet through the whole network; the hot path is the 12
+  MSDeformAttn layers (fused snippet kernels, one launch per layer).  Backbone and Linear layers
+  are stock cuDNN/cuBLAS (out of scope per north_star) in torch's default fp32 settings.
+
+Output: ONE JSON line (rank 0).  `value` = snippets/s with inputs resident in HBM; `e2e` = same
+through the public call with pinned-host inputs (H2D + D2H inside the timed region);
+`roofline` = the dominant kernel (fused encoder-layer forward) timed with CUDA events on its
+stream; `cpu_baseline` = the reference's PyTorch/grid_sample formulation (oracle port) on the
+host cores for a bounded sample.  --impl reference prints the CPU arm as its own line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "snippets_per_sec_T4_600x800"
+UNIT = "snippets/s"
+WORKLOAD = "snipper_T4_enc6_dec6_h384_M8_L3_P4_infer_b1_600x800"
+H, W, T = 600, 800, 4
+N_INPUTS = 4  # distinct synthetic snippets rotated through the steps
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_snippets(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(1, 3 * T, H, W, generator=g) for _ in range(n)]  # frames are /255 floats in [0,1]
+
+
+def pack_result(out):
+    """The step's result a caller reads back: final-layer predictions."""
+    return torch.cat([out["pred_logits"].flatten(), out["pred_kpts2d"].flatten(), out["pred_depth"].flatten()])
+
+
+def fused_layer_bytes(dims, e=4):
+    """Algorithmic bytes of one fused layer launch (fused-snippet accounting):
+    value read once, offsets(2)+logits(1) once per sample, output once."""
+    N, T2, T1, S, M, D, L, Lq, P = dims
+    samples = N * T1 * Lq * M * L * P
+    value = min(N * T2 * S * M * D, 4 * samples * D * 3)
+    return e * (value + 3 * samples + N * T1 * Lq * M * D)
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s=150.0):
+    """The reference's CPU path for this workload: the same network with the attention computed
+    by the PyTorch grid_sample formulation (oracle/torch_ref.py restates
+    ms_deform_attn_core_pytorch + the per-frame module loop).  One step = one full snippet."""
+    from oracle import torch_ref
+    from snipper_b200.harness.snipper_net import build_snipper
+    torch.manual_seed(42)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_snipper(torch_ref.SnippetMSDeformAttnRef).eval()
+    xs = synthetic_snippets(2, seed=1)
+    times = []
+    t_begin = time.perf_counter()
+    with torch.no_grad():
+        n_warm = min(warmup, 1)
+        for i in range(n_warm + steps):
+            t0 = time.perf_counter()
+            out, _ = model(xs[i % len(xs)])
+            pack_result(out)
+            dt = time.perf_counter() - t0
+            if i >= n_warm:
+                times.append(dt)
+            if times and (time.perf_counter() - t_begin) + dt > budget_s:
+                break
+    return times, cores
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    times, cores = cpu_reference_run(args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    v = 1e3 / ms
+    sample = "%d full snippet forward(s), batch 1, whole network, MSDA via grid_sample" % len(times)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "cpu", "threads": cores},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import snipper_b200
+    from snipper_b200 import ops
+    from snipper_b200.harness.snipper_net import build_snipper
+
+    args.warmup = max(args.warmup, 3)
+    torch.manual_seed(42)  # reference main.py:48
+    model = build_snipper(snipper_b200.MSDeformAttn).to(dev).eval()
+    host = [x.pin_memory() for x in synthetic_snippets(N_INPUTS, seed=1000 + rank)]  # every rank its own shard
+    resident = [x.to(dev) for x in host]
+    h2d_bytes = host[0].numel() * host[0].element_size()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- build the step functions -------------------------------------------------------
+    use_graph = not args.no_graph
+    static_in = torch.empty_like(resident[0])
+    with torch.no_grad():
+        for i in range(2):  # lazy init (cuDNN autotune, cuBLAS handles) before capture
+            out, _ = model(resident[i])
+            result = pack_result(out)
+    d2h_bytes = result.numel() * result.element_size()
+    host_out = torch.empty(result.shape, dtype=result.dtype).pin_memory()
+    graph, launches_per_step = None, None
+    ops.STATS.reset()
+    if use_graph:
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                out, _ = model(static_in)
+                static_result = pack_result(out)
+            launches_per_step = ops.STATS.launches
+        except Exception as e:  # fall back to eager timing, say so in config
+            print("[bench] CUDA graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
+            graph, use_graph = None, False
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        with torch.no_grad():
+            if graph is not None:
+                static_in.copy_(resident[i % N_INPUTS])  # device->device, keeps inputs rotating
+                graph.replay()
+                return static_result
+            out, _ = model(resident[i % N_INPUTS])
+            return pack_result(out)
+
+    def step_e2e(i):
+        with torch.no_grad():
+            if graph is not None:
+                static_in.copy_(host[i % N_INPUTS], non_blocking=True)
+                graph.replay()
+                host_out.copy_(static_result, non_blocking=True)
+            else:
+                x = host[i % N_INPUTS].to(dev, non_blocking=True)
+                out, _ = model(x)
+                host_out.copy_(pack_result(out), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+        return host_out
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            step_fn(warmup + i)
+        e.record()
+        barrier()
+        return max_over_ranks(s.elapsed_time(e))
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ops.STATS.reset()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    eager_launches = ops.STATS.launches
+    ms_e2e_total = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    if launches_per_step is None:
+        launches_per_step = eager_launches // (args.steps + args.warmup)
+
+    # ---- roofline of the dominant kernel: events around every fused-layer launch, eager steps ----
+    ops.STATS.reset()
+    ops.STATS.timing = True
+    with torch.no_grad():
+        for i in range(args.steps):
+            model(resident[i % N_INPUTS])
+    torch.cuda.synchronize()
+    ops.STATS.timing = False
+    per_kernel = ops.STATS.kernel_ms()
+    (dom_tag, dom_dims), dom_ms = max(per_kernel.items(), key=lambda kv: sum(kv[1]))
+    dom_avg_ms = sum(dom_ms) / len(dom_ms)
+    msda_ms_per_step = sum(sum(v) for v in per_kernel.values()) / args.steps
+    peak, peak_src = measured_peak()
+    alg_bytes = fused_layer_bytes(dom_dims)
+    achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get("snippet_forward_encoder_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "snippets_per_gpu_per_step": 1, "parallelism": "snippet-sharded x%d, no collective" % world,
+                   "launch": "cuda_graph_replay" if graph is not None else "eager",
+                   "l2": "working set per step (171 MB weights + >1 GB activations) exceeds the 126 MB L2; %d distinct inputs rotated" % N_INPUTS,
+                   "weights": "random init (seed 42): sampling offsets are the fixed per-head grid, best-case gather locality",
+                   "msda_ms_per_step_eager_events": msda_ms_per_step},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e_total / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "msda_snippet_fwd_kernel<12,16> (%s %s)" % (dom_tag, "x".join(map(str, dom_dims))),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "avg_launch_ms": dom_avg_ms, "launches_timed": len(dom_ms),
+                     "how": "CUDA events on the launching stream around each launch, eager steps after the timed region"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_reference_run(1, 0)
+        v = len(times) / sum(times)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d full snippet forward, batch 1, whole network on host cores, MSDA via grid_sample (oracle port of the reference's PyTorch path)" % len(times)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,51 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class LaunchStats:
+    """Counts kernel launches issued through the C ABI and, when ``timing`` is on, brackets each
+    launch with CUDA events on the launching stream (bench.py's roofline measurement)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.events = []  # (tag, dims, start_event, end_event)
+
+    def reset(self):
+        self.launches = 0
+        self.events = []
+
+    def kernel_ms(self):
+        """tag -> list of per-launch durations in ms (call after a device synchronize)."""
+        out = {}
+        for tag, dims, s, e in self.events:
+            out.setdefault((tag, dims), []).append(s.elapsed_time(e))
+        return out
+
+
+STATS = LaunchStats()
+
+
+class _Launch:
+    """with _Launch(tag, dims, device, n_kernels): <C call>"""
+
+    def __init__(self, tag, dims, device, n_kernels=1):
+        self.tag, self.dims, self.device, self.n = tag, dims, device, n_kernels
+
+    def __enter__(self):
+        if STATS.timing:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        STATS.launches += self.n
+        if STATS.timing:
+            self.e.record(torch.cuda.current_stream(self.device))
+            STATS.events.append((self.tag, self.dims, self.s, self.e))
+        return False
+
+
 def _require_cuda(t: Tensor, name: str) -> None:
     if not t.is_cuda:
         # reference models/ops/src/ms_deform_attn.h:38,60
@@ -91,7 +136,7 @@ def msda_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tenso
     N, S, M, D, L, Lq, P = _check_percall(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     vbs = _value_batch_stride(value)
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Launch("msda_forward", (N, S, M, D, L, Lq, P), value.device):
         st = capi.lib().msda_forward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
@@ -127,6 +172,7 @@ def msda_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tens
             ws_bytes = capi.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dt, flags)
             ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=value.device)
         ws_ptr = 0 if ws is None else (ws.data_ptr() + 255) // 256 * 256
+        STATS.launches += 1
         st = capi.lib().msda_backward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
@@ -219,7 +265,7 @@ def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Te
     sn, st = _value_strides5(value)
     ref, rsn, rst = _ref_strides(reference_points)
     out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Launch("snippet_forward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
         status = capi.lib().msda_snippet_forward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), out.data_ptr(),
@@ -248,7 +294,7 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
     grad_value = torch.empty((N, T2, S, M, D), dtype=value.dtype, device=value.device)
     grad_offsets = torch.empty_like(offsets)
     grad_logits = torch.empty_like(logits)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Launch("snippet_backward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
         status = capi.lib().msda_snippet_backward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),

@@ -1,0 +1,130 @@
+"""CPU tests of the host-side logic: C-ABI surface, error behaviour without a GPU, module
+contract (state-dict keys, init), custom-op fake kernels, and the N>1 path on gloo (world 2)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import snipper_b200
+from snipper_b200 import capi, sharding
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "msda_b200.h")).read()
+    declared = set(re.findall(r"MSDA_API\s+[\w\s\*]*?\b(msda_\w+)\s*\(", header))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert capi.lib().msda_abi_version() == capi.MSDA_ABI_VERSION
+    assert b"im2col_step" in capi.lib().msda_error_string(capi.MSDA_ERR_IM2COL_STEP)
+
+
+def test_argument_validation_needs_no_gpu():
+    """Validation happens before any launch, so these calls are safe on a CPU-only box."""
+    L = capi.lib()
+    # null pointers
+    assert L.msda_forward(0, 0, 0, 0, 0, 0, 1, 4, 2, 16, 1, 3, 2, 0, 64, 0, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
+    # im2col_step: batch 3, step 2 -> 3 % 2 != 0 (reference ms_deform_attn_cuda.cu:50-52)
+    assert L.msda_forward(8, 8, 8, 8, 8, 8, 3, 4, 2, 16, 1, 3, 2, 0, 2, 0, 0) == capi.MSDA_ERR_IM2COL_STEP
+    # bad dtype tag
+    assert L.msda_forward(8, 8, 8, 8, 8, 8, 1, 4, 2, 16, 1, 3, 2, 0, 64, 7, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    # empty problems are a no-op
+    assert L.msda_forward(0, 0, 0, 0, 0, 0, 0, 4, 2, 16, 1, 3, 2, 0, 64, 0, 0) == capi.MSDA_OK
+    assert L.msda_set_tuning(b"pairs_d48", 7) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert L.msda_set_tuning(b"pairs_d48", 16) == capi.MSDA_OK
+    assert L.msda_backward_workspace_bytes(1, 100, 8, 48, 3, 100, 4, 0, 0) == 0
+    assert L.msda_backward_workspace_bytes(1, 100, 8, 48, 3, 100, 4, 0, capi.MSDA_FLAG_DETERMINISTIC) > 0
+
+
+def test_cpu_tensors_raise_like_the_reference():
+    shim = snipper_b200.install_extension_shim()
+    args = (torch.zeros(1, 4, 2, 16), torch.tensor([[2, 2]]), torch.tensor([0]),
+            torch.zeros(1, 3, 2, 1, 2, 2), torch.zeros(1, 3, 2, 1, 2))
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):  # ms_deform_attn.h:38
+        shim.ms_deform_attn_forward(*args, 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        shim.ms_deform_attn_backward(*args, torch.zeros(1, 3, 32), 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        snipper_b200.MSDeformAttnFunction.apply(*args, 64)
+    import MultiScaleDeformableAttention as by_name  # importable under the reference's module name
+    assert by_name is shim
+
+
+def test_fake_kernels_give_shapes_without_a_device():
+    v = torch.empty(2, 50, 8, 48, device="meta")
+    sh = torch.empty(3, 2, dtype=torch.long, device="meta")
+    lsi = torch.empty(3, dtype=torch.long, device="meta")
+    loc = torch.empty(2, 7, 8, 3, 4, 2, device="meta")
+    att = torch.empty(2, 7, 8, 3, 4, device="meta")
+    out = torch.ops.snipper_b200.msda_forward(v, sh, lsi, loc, att, 64)
+    assert out.shape == (2, 7, 384)
+    gv, gl, ga = torch.ops.snipper_b200.msda_backward(v, sh, lsi, loc, att, out, 64, False)
+    assert gv.shape == v.shape and gl.shape == loc.shape and ga.shape == att.shape
+    v5 = torch.empty(2, 4, 50, 8, 48, device="meta")
+    off = torch.empty(2, 6, 7, 8, 3, 4, 2, device="meta")
+    lg = torch.empty(2, 6, 7, 8, 3, 4, device="meta")
+    ref = torch.empty(2, 6, 7, 3, 2, device="meta")
+    assert torch.ops.snipper_b200.snippet_forward(v5, sh, lsi, off, lg, ref, 4).shape == (2, 6, 7, 384)
+
+
+def test_module_contract_matches_reference_checkpoint_layout():
+    g = load_golden("module_decoder")
+    want = sorted(k[3:] for k in g if k.startswith("sd."))
+    mod = snipper_b200.MSDeformAttn(48, 3, 4, 4, 4, "decoder", False, True)
+    assert sorted(mod.state_dict().keys()) == want
+    assert all(m is mod.sampling_offsets[0] for m in mod.sampling_offsets)  # aliased slots (:68-71)
+    # initialisation (reference :78-97): zero weights, per-head direction grid scaled by (p+1)
+    assert mod.sampling_offsets[0].weight.abs().max() == 0 and mod.attention_weights[0].bias.abs().max() == 0
+    b = mod.sampling_offsets[0].bias.view(4, 3, 4, 2)
+    assert torch.allclose(b[0, :, :, 0], torch.tensor([1., 2., 3., 4.]).expand(3, 4))
+    assert torch.allclose(b[1, 0, 2], torch.tensor([0., 3.]), atol=1e-6)
+    assert snipper_b200.modules.neighbour_frames(0, 4, 4) == [0, 1]
+    assert snipper_b200.modules.neighbour_frames(2, 4, 4) == [1, 2, 3]
+    assert snipper_b200.modules.neighbour_frames(5, 4, 4) == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        snipper_b200.MSDeformAttn(50, 3, 8, 4)
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 7, 8, 9, 64):
+        for world in (1, 2, 3, 8):
+            got = [i for r in range(world) for i in range(*sharding.shard_range(n, r, world))]
+            assert got == list(range(n))
+            sizes = [b - a for a, b in (sharding.shard_range(n, r, world) for r in range(world))]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(9, rank, world)
+    elapsed = 1.0 + rank  # rank 1 is the straggler
+    thr = sharding.aggregate_throughput(hi - lo, elapsed)
+    mx = sharding.max_over_ranks(elapsed)
+    ranges = [None] * world
+    dist.all_gather_object(ranges, (lo, hi))
+    q.put((rank, thr, mx, ranges))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_timing_reduction_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, thr, mx, ranges in res:
+        assert mx == 2.0                      # slowest rank
+        assert abs(thr - 9 / 2.0) < 1e-12     # all items / slowest time
+        assert ranges == [(0, 5), (5, 9)]
