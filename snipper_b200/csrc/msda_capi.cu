@@ -170,7 +170,8 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
         return cuda_status(msda::launch_backward_deterministic_f32(
             (const float *)value, spatial_shapes, level_start_index, (const float *)sampling_loc,
             (const float *)attn_weight, (const float *)grad_output, (float *)grad_value,
-            (float *)grad_sampling_loc, (float *)grad_attn_weight, d, workspace, s));
+            (float *)grad_sampling_loc, (float *)grad_attn_weight, d, workspace, s,
+            (flags & MSDA_FLAG_ACCUMULATE_VALUE) != 0));
     }
     if (msda::fast_path_ok(d) && aligned16(value) && aligned16(grad_output) && aligned16(grad_value))
         return cuda_status(msda::launch_backward_fast_f32(

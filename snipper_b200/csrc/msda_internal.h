@@ -48,7 +48,8 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
                                               const int64_t *lsi, const float *loc,
                                               const float *attn, const float *grad_out,
                                               float *grad_value, float *grad_loc, float *grad_attn,
-                                              const OpDims &d, void *workspace, cudaStream_t stream);
+                                              const OpDims &d, void *workspace, cudaStream_t stream,
+                                              bool accumulate);
 
 // ---- fused snippet op (msda_snippet.cu) ----
 bool snippet_ok(const SnippetDims &d);

@@ -52,17 +52,6 @@ __device__ __forceinline__ TileCoord tile_of_block(int M, int Lq, int pairs)
     return t;
 }
 
-struct __align__(16) FwdRec {
-    int4 off;   // float4-index offsets of the four cells relative to (batch base + m*D), or -1
-    float4 w;   // bilinear weight x attention weight per corner
-};
-
-struct __align__(16) BwdRec {
-    int4 off;
-    float lx, ly, a;
-    int level;
-};
-
 template <int LANES, int PAIRS>
 __global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
@@ -74,12 +63,12 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     using Cfg = FastCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FwdRec *rec = reinterpret_cast<FwdRec *>(smem_raw);
+    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int LP = L * P;
     const TileCoord tc = tile_of_block(M, Lq, Cfg::PAIRS);
-    const int cell_stride = M * LANES;  // float4 units between consecutive cells
+    const int cs = M * LANES;  // float4 units between consecutive cells
 
     load_level_table(lv, shapes, lsi, L);
     __syncthreads();
@@ -98,45 +87,33 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = i / n;
             const int lp = lp0 + (i - spl * n);
-            FwdRec r;
-            r.off = make_int4(-1, -1, -1, -1);
-            r.w = make_float4(0.f, 0.f, 0.f, 0.f);
+            Rec r = empty_rec();
             if (tc.q0 + spl < Lq) {
                 const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
-                const float a = __ldg(attn + si);
                 const int l = lp / P;
-                const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
-                const float hx = 1.f - s.lx, hy = 1.f - s.ly;
-                r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
-                r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
-                r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
-                r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
-                r.w = make_float4(hy * hx * a, hy * s.lx * a, s.ly * hx * a, s.ly * s.lx * a);
+                r = make_rec(make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]), __ldg(attn + si));
             }
             rec[i] = r;
         }
         __syncthreads();
         // ---- phase 2: gather ----
         if (live) {
-            const FwdRec *my = rec + pl * n;
+            const Rec *my = rec + pl * n;
+            LevelWalker lw(lv, lp0, P, L, cs);
 #pragma unroll 4
             for (int j = 0; j < n; ++j) {
-                const int4 o = my[j].off;
-                const float4 w = my[j].w;
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-                if (o.x >= 0) v0 = ldg4(vbase + o.x);
-                if (o.y >= 0) v1 = ldg4(vbase + o.y);
-                if (o.z >= 0) v2 = ldg4(vbase + o.z);
-                if (o.w >= 0) v3 = ldg4(vbase + o.w);
-                acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y);
-                acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
-                acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y);
-                acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
-                acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y);
-                acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
-                acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y);
-                acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
+                const Rec r = my[j];
+                int o0;
+                float4 v0, v1, v2, v3;
+                gather4(r, vbase, cs, lw.wcs, o0, v0, v1, v2, v3);
+                const float hx = 1.f - r.lx, hy = 1.f - r.ly;
+                const float ahy = r.a * hy, aly = r.a * r.ly;
+                fma4(acc, ahy * hx, v0);
+                fma4(acc, ahy * r.lx, v1);
+                fma4(acc, aly * hx, v2);
+                fma4(acc, aly * r.lx, v3);
+                lw.next(lv);
             }
         }
         if (lp0 + cl < LP) __syncthreads();  // records are reused by the next pass
@@ -144,7 +121,9 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     if (live) reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
 }
 
-template <int LANES, int PAIRS>
+// SCATTER == false: grad_sampling_loc / grad_attn_weight only (deterministic mode computes
+// grad_value separately, msda_deterministic.cu)
+template <int LANES, int PAIRS, bool SCATTER>
 __global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -157,13 +136,13 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     using Cfg = FastCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdRec *rec = reinterpret_cast<BwdRec *>(smem_raw);
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(BwdRec) * Cfg::PAIRS * cl);  // [rec][SUBS][3]
+    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(Rec) * Cfg::PAIRS * cl);  // [rec][SUBS][3]
 
     const int tid = threadIdx.x;
     const int LP = L * P;
     const TileCoord tc = tile_of_block(M, Lq, Cfg::PAIRS);
-    const int cell_stride = M * LANES;
+    const int cs = M * LANES;
 
     load_level_table(lv, shapes, lsi, L);
     __syncthreads();
@@ -186,44 +165,39 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = i / n;
             const int lp = lp0 + (i - spl * n);
-            BwdRec r;
-            r.off = make_int4(-1, -1, -1, -1);
-            r.lx = 0.f; r.ly = 0.f; r.a = 0.f; r.level = 0;
+            Rec r = empty_rec();
             if (tc.q0 + spl < Lq) {
                 const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
                 const int l = lp / P;
-                const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
-                r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
-                r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
-                r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
-                r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
-                r.lx = s.lx; r.ly = s.ly; r.a = __ldg(attn + si); r.level = l;
+                r = make_rec(make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]), __ldg(attn + si));
             }
             rec[i] = r;
         }
         __syncthreads();
         // ---- phase 2: gather + scatter; every thread runs it (full-mask shuffles) ----
         {
-            const BwdRec *my = rec + pl * n;
+            const Rec *my = rec + pl * n;
             float *mypart = part + (size_t)(pl * n) * (Cfg::SUBS * 3) + sub * 3;
+            LevelWalker lw(lv, lp0, P, L, cs);
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
-                const int4 o = my[j].off;
-                const float lx = my[j].lx, ly = my[j].ly, a = my[j].a;
+                const Rec r = my[j];
+                int o0;
+                float4 v0, v1, v2, v3;
+                gather4(r, vbase, cs, lw.wcs, o0, v0, v1, v2, v3);
+                const float lx = r.lx, ly = r.ly, a = r.a;
                 const float hx = 1.f - lx, hy = 1.f - ly;
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-                if (o.x >= 0) v0 = ldg4(vbase + o.x);
-                if (o.y >= 0) v1 = ldg4(vbase + o.y);
-                if (o.z >= 0) v2 = ldg4(vbase + o.z);
-                if (o.w >= 0) v3 = ldg4(vbase + o.w);
-                // grad_value: w_k * A * G  (vector reductions, one per corner per lane)
-                const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
                 const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
-                if (o.x >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.x), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
-                if (o.y >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.y), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
-                if (o.z >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.z), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
-                if (o.w >= 0) red_add_v4(reinterpret_cast<float *>(gvbase + o.w), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+                if (SCATTER) {
+                    // grad_value: w_k * A * G  (vector reductions, one per corner per lane)
+                    const unsigned mask = r.pk >> 28;
+                    const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+                    if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gvbase + o0), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
+                    if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gvbase + o0 + cs), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
+                    if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gvbase + o0 + lw.wcs), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
+                    if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gvbase + o0 + lw.wcs + cs), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+                }
                 // per-sample scalars: <G,val>, <G,dval/dx>, <G,dval/dy> over this lane's channels
                 float4 val, dxv, dyv;
                 val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
@@ -249,6 +223,7 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
                     float *dst = mypart + j * (Cfg::SUBS * 3);
                     dst[0] = pa; dst[1] = px; dst[2] = py;
                 }
+                lw.next(lv);
             }
         }
         __syncthreads();
@@ -261,11 +236,12 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
                 float pa = 0.f, px = 0.f, py = 0.f;
 #pragma unroll
                 for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
-                const BwdRec r = rec[i];
+                const float a = rec[i].a;
+                const int l = lp / P;
                 const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
                 grad_attn[si] = pa;
                 reinterpret_cast<float2 *>(grad_loc)[si] =
-                    make_float2((float)lv.W[r.level] * r.a * px, (float)lv.H[r.level] * r.a * py);
+                    make_float2((float)lv.W[l] * a * px, (float)lv.H[l] * a * py);
             }
         }
         if (lp0 + cl < LP) __syncthreads();
@@ -279,6 +255,7 @@ bool fast_path_ok(const OpDims &d)
     if (d.value_batch_stride % 4 != 0) return false;
     // in-kernel 32-bit indices: float4 cell offsets, pair and sample counters
     if ((int64_t)d.S * d.M * (d.D / 4) >= (int64_t)INT32_MAX) return false;
+    if ((int64_t)d.S >= (int64_t)kRecBias - 65536) return false;  // packed cell index (Rec::pk)
     if ((int64_t)d.N * d.Lq * d.M >= (int64_t)INT32_MAX / 64) return false;
     return true;
 }
@@ -294,13 +271,13 @@ static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, co
     const int LP = d.L * d.P;
     const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
     const int grid = d.N * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = sizeof(FwdRec) * Cfg::PAIRS * cl;
+    const size_t smem = sizeof(Rec) * Cfg::PAIRS * cl;
     msda_fwd_fast_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
         value, shapes, lsi, loc, attn, out, d.M, d.L, d.P, d.Lq, d.value_batch_stride, cl);
     return cudaGetLastError();
 }
 
-template <int LANES, int PAIRS>
+template <int LANES, int PAIRS, bool SCATTER = true>
 static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *loc, const float *attn, const float *grad_out,
                                    float *grad_value, float *grad_loc, float *grad_attn,
@@ -310,8 +287,8 @@ static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, co
     const int LP = d.L * d.P;
     const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
     const int grid = d.N * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = (sizeof(BwdRec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * cl;
-    msda_bwd_fast_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
+    const size_t smem = (sizeof(Rec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * cl;
+    msda_bwd_fast_kernel<LANES, PAIRS, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
         value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d.S, d.M, d.L,
         d.P, d.Lq, d.value_batch_stride, cl);
     return cudaGetLastError();
@@ -403,7 +380,7 @@ msda_bwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__
                         T *__restrict__ grad_value, T *__restrict__ grad_loc,
                         T *__restrict__ grad_attn,
                         int S, int M, int D, int L, int P, int Lq, int64_t total_pairs,
-                        int64_t value_batch_stride)
+                        int64_t value_batch_stride, bool scatter)
 {
     __shared__ LevelTable lv;
     load_level_table(lv, shapes, lsi, L);
@@ -434,10 +411,12 @@ msda_bwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__
                 const T v2 = s.cell[2] >= 0 ? vb[s.cell[2] * cs + c] : (T)0;
                 const T v3 = s.cell[3] >= 0 ? vb[s.cell[3] * cs + c] : (T)0;
                 const T ga = gc * a;
-                if (s.cell[0] >= 0) atomicAdd(gvb + s.cell[0] * cs + c, w0 * ga);
-                if (s.cell[1] >= 0) atomicAdd(gvb + s.cell[1] * cs + c, w1 * ga);
-                if (s.cell[2] >= 0) atomicAdd(gvb + s.cell[2] * cs + c, w2 * ga);
-                if (s.cell[3] >= 0) atomicAdd(gvb + s.cell[3] * cs + c, w3 * ga);
+                if (scatter) {
+                    if (s.cell[0] >= 0) atomicAdd(gvb + s.cell[0] * cs + c, w0 * ga);
+                    if (s.cell[1] >= 0) atomicAdd(gvb + s.cell[1] * cs + c, w1 * ga);
+                    if (s.cell[2] >= 0) atomicAdd(gvb + s.cell[2] * cs + c, w2 * ga);
+                    if (s.cell[3] >= 0) atomicAdd(gvb + s.cell[3] * cs + c, w3 * ga);
+                }
                 pa += gc * (w0 * v0 + w1 * v1 + w2 * v2 + w3 * v3);
                 px += gc * (hy * (v1 - v0) + s.ly * (v3 - v2));
                 py += gc * (hx * (v2 - v0) + s.lx * (v3 - v1));
@@ -472,10 +451,10 @@ cudaError_t launch_forward_generic(const T *value, const int64_t *shapes, const 
 }
 
 template <typename T>
-cudaError_t launch_backward_generic(const T *value, const int64_t *shapes, const int64_t *lsi,
-                                    const T *loc, const T *attn, const T *grad_out,
-                                    T *grad_value, T *grad_loc, T *grad_attn, const OpDims &d,
-                                    cudaStream_t stream)
+static cudaError_t launch_backward_generic_impl(const T *value, const int64_t *shapes, const int64_t *lsi,
+                                                const T *loc, const T *attn, const T *grad_out,
+                                                T *grad_value, T *grad_loc, T *grad_attn, const OpDims &d,
+                                                cudaStream_t stream, bool scatter)
 {
     const int64_t total_pairs = (int64_t)d.N * d.Lq * d.M;
     if (total_pairs == 0) return cudaSuccess;
@@ -484,8 +463,37 @@ cudaError_t launch_backward_generic(const T *value, const int64_t *shapes, const
     msda_bwd_generic_kernel<T><<<grid, 256, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out,
                                                          grad_value, grad_loc, grad_attn, d.S, d.M,
                                                          d.D, d.L, d.P, d.Lq, total_pairs,
-                                                         d.value_batch_stride);
+                                                         d.value_batch_stride, scatter);
     return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_backward_generic(const T *value, const int64_t *shapes, const int64_t *lsi,
+                                    const T *loc, const T *attn, const T *grad_out,
+                                    T *grad_value, T *grad_loc, T *grad_attn, const OpDims &d,
+                                    cudaStream_t stream)
+{
+    return launch_backward_generic_impl<T>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc,
+                                           grad_attn, d, stream, true);
+}
+
+// grad_sampling_loc / grad_attn_weight only (used by the deterministic mode)
+cudaError_t launch_backward_no_scatter_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                           const float *loc, const float *attn, const float *grad_out,
+                                           float *grad_loc, float *grad_attn, const OpDims &d,
+                                           cudaStream_t stream)
+{
+    if (d.N * d.Lq * d.M == 0) return cudaSuccess;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(value) & 15u) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0;
+    if (fast_path_ok(d) && vec_ok) {
+        float *none = nullptr;
+#define CALL(LN, PR) \
+    launch_bwd_fast<LN, PR, false>(value, shapes, lsi, loc, attn, grad_out, none, grad_loc, grad_attn, d, stream)
+        MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+    }
+    return launch_backward_generic_impl<float>(value, shapes, lsi, loc, attn, grad_out, nullptr, grad_loc,
+                                               grad_attn, d, stream, false);
 }
 
 template cudaError_t launch_forward_generic<float>(const float *, const int64_t *, const int64_t *,

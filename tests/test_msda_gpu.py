@@ -303,3 +303,57 @@ def test_matches_vendored_cuda_op(full_case):
     assert rel_err(grads[0], gv_ref) < BWD_TOL
     assert rel_err(grads[1], gl_ref) < BWD_TOL
     assert rel_err(grads[2], ga_ref) < BWD_TOL
+
+
+# ---------------------------------------------------------------- deterministic two-pass backward
+@pytest.mark.parametrize("D,Lq", [(48, None), (30, 37)])
+def test_deterministic_backward_is_bit_reproducible(D, Lq):
+    """MSDA_FLAG_DETERMINISTIC: same bits run to run, still within the backward tolerance."""
+    import snipper_b200
+    c = make_case(2, 8 if D == 48 else 3, D, SNIPPER_SMALL_LEVELS, 4, Lq=Lq, regime="local", sigma_px=1.5, seed=21)
+    dev = "cuda:0"
+    args = [c[k].to(dev) for k in ("value", "shapes", "lsi", "loc", "attn", "grad_out")]
+    runs = [torch.ops.snipper_b200.msda_backward(*args, 64, True) for _ in range(3)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+    a64 = (c["value"].double(), c["shapes"], c["lsi"], c["loc"].double(), c["attn"].double())
+    ref = c_oracle.backward(*a64, c["grad_out"].double())
+    for got, want in zip(runs[0], ref):
+        assert rel_err(got, want) < BWD_TOL
+    # and through autograd with the process-wide switch
+    snipper_b200.set_deterministic(True)
+    try:
+        _, g1 = cuda_fwd_bwd(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"], c["grad_out"])
+        _, g2 = cuda_fwd_bwd(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"], c["grad_out"])
+    finally:
+        snipper_b200.set_deterministic(False)
+    assert all(torch.equal(x, y) for x, y in zip(g1, g2))
+    assert torch.equal(g1[0], runs[0][0].cpu())
+
+
+def test_deterministic_full_size(full_case):
+    dev = "cuda:0"
+    args = [full_case[k].to(dev) for k in ("value", "shapes", "lsi", "loc", "attn", "grad_out")]
+    a = torch.ops.snipper_b200.msda_backward(*args, 64, True)
+    b = torch.ops.snipper_b200.msda_backward(*args, 64, True)
+    fast = torch.ops.snipper_b200.msda_backward(*args, 64, False)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    for x, y in zip(a, fast):
+        assert rel_err(x, y) < BWD_TOL
+
+
+def test_pile_up_on_one_cell_long_list_path():
+    """Every query samples the same location: one cell receives thousands of contributions
+    (the in-kernel list spills past shared memory; exercises the long-list path)."""
+    c = make_case(1, 2, 16, [(4, 4)], 2, Lq=300, regime="uniform", seed=2)
+    c["loc"] = torch.full_like(c["loc"], 0.4)
+    dev = "cuda:0"
+    args = [c[k].to(dev) for k in ("value", "shapes", "lsi", "loc", "attn", "grad_out")]
+    a = torch.ops.snipper_b200.msda_backward(*args, 64, True)
+    b = torch.ops.snipper_b200.msda_backward(*args, 64, True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    ref = c_oracle.backward(c["value"].double(), c["shapes"], c["lsi"], c["loc"].double(), c["attn"].double(),
+                            c["grad_out"].double())
+    for got, want in zip(a, ref):
+        assert rel_err(got, want) < BWD_TOL
