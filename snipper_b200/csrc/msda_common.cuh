@@ -70,58 +70,6 @@ __device__ __forceinline__ Sample<real> make_sample(real u, real v, int H, int W
     return s;
 }
 
-// 16-byte per-sample record parked in shared memory by phase 1 and broadcast-read (one LDS.128)
-// by the lanes of the pair in phase 2: corner offsets and bilinear weights are rebuilt in
-// registers.  (The first version stored 4 offsets + 4 weights = 32 bytes; the two LDS.128 per
-// point were 30 % of the L1 data-pipe wavefronts, profiles/r01_run3_*.)
-constexpr int kRecBias = 1 << 27;  // base + bias fits 28 bits: needs S < 2^27 cells
-
-struct __align__(16) Rec {
-    unsigned pk;  // (base + kRecBias) | mask << 28
-    float lx, ly;
-    float a;      // attention weight (0 for inactive / padded records)
-};
-
-__device__ __forceinline__ Rec make_rec(const Sample<float> &s, float a)
-{
-    Rec r;
-    r.pk = (unsigned)(s.base + kRecBias) | ((unsigned)s.mask << 28);
-    r.lx = s.lx; r.ly = s.ly; r.a = a;
-    return r;
-}
-
-__device__ __forceinline__ Rec empty_rec()
-{
-    Rec r;
-    r.pk = (unsigned)kRecBias; r.lx = 0.f; r.ly = 0.f; r.a = 0.f;
-    return r;
-}
-
-// Walks the level of consecutive samples (level-major order, P points per level) without a
-// division per sample; exposes W_l * cell_stride for the row offset of corners 2 and 3.
-struct LevelWalker {
-    int l, pc, P, L, cs, wcs;
-    __device__ __forceinline__ LevelWalker(const LevelTable &lv, int lp0, int P_, int L_, int cs_)
-        : l(lp0 / P_), pc(lp0 % P_), P(P_), L(L_), cs(cs_), wcs(lv.W[lp0 / P_] * cs_) {}
-    __device__ __forceinline__ void next(const LevelTable &lv)
-    {
-        if (++pc == P) { pc = 0; ++l; if (l < L) wcs = lv.W[l] * cs; }
-    }
-};
-
-// gather the four corners of a record for this lane (predicated 128-bit loads)
-__device__ __forceinline__ void gather4(const Rec &r, const float4 *vbase, int cs, int wcs, int &o0,
-                                        float4 &v0, float4 &v1, float4 &v2, float4 &v3)
-{
-    const unsigned mask = r.pk >> 28;
-    o0 = ((int)(r.pk & 0x0fffffffu) - kRecBias) * cs;
-    v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0; v2 = v0; v3 = v0;
-    if (mask & 1u) v0 = __ldg(vbase + o0);
-    if (mask & 2u) v1 = __ldg(vbase + o0 + cs);
-    if (mask & 4u) v2 = __ldg(vbase + o0 + wcs);
-    if (mask & 8u) v3 = __ldg(vbase + o0 + wcs + cs);
-}
-
 __device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v)
 {
     acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);

@@ -18,233 +18,188 @@
 //  * GENERIC (float / double, any D): straightforward one-thread-per-output-element forward
 //      and one-warp-per-pair backward; used for fp64 parity tests and odd channel counts
 //      (the reference's test list 30, 71, 1025, ... models/ops/test.py:85).
-#include "msda_common.cuh"
+#include "msda_fast.cuh"
 #include "msda_internal.h"
 
 namespace msda {
 
 // ------------------------------------------------------------------------------------------
-// FAST fp32 path
+// FAST fp32 path (see msda_fast.cuh for the CTA organisation)
 // ------------------------------------------------------------------------------------------
-// A CTA owns a TILE: PAIRS consecutive queries of ONE head of one batch item.  Consecutive
-// queries are neighbouring pixels in the encoder, so the cells they gather overlap and are served
-// from L1 (the first version mapped a CTA to 2 queries x 8 heads: 9 % L1 hit rate, bound by the
-// L2->L1 fill path; see profiles/r01_run1_*).  blockIdx -> (n, query tile, m) with m fastest.
+// grid = (M, query tiles, N): a CTA owns PAIRS consecutive queries of ONE head.  Consecutive
+// queries are neighbouring pixels in the encoder, so the cells they gather overlap and hit in L1.
 template <int LANES, int PAIRS_>
 struct FastCfg {
     static constexpr int PAIRS = PAIRS_;
     static constexpr int THREADS = PAIRS * LANES;
-    static constexpr int SUBS = LANES / 4;                              // 4-lane shuffle groups
-    static constexpr int CHUNK = (512 / PAIRS) < 32 ? (512 / PAIRS) : 32;  // samples per pair per pass
+    static constexpr int SUBS = LANES / 4;                                 // 4-lane shuffle groups
+    static constexpr int CHUNK = (512 / PAIRS) < 32 ? (512 / PAIRS) : 32;  // samples per query per pass
     static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
-struct TileCoord { int n, q0, m; };
+struct FastArgs {
+    int M, L, P, Lq, S;
+    int cell_bytes;            // M * D * 4
+    int cl;                    // samples per query per pass (<= CHUNK)
+    unsigned magic_cl, magic_P;
+    int64_t value_batch_stride;  // elements
+};
 
-__device__ __forceinline__ TileCoord tile_of_block(int M, int Lq, int pairs)
-{
-    const int tiles = (Lq + pairs - 1) / pairs;
-    int b = blockIdx.x;
-    TileCoord t;
-    t.m = b % M; b /= M;
-    t.q0 = (b % tiles) * pairs;
-    t.n = b / tiles;
-    return t;
-}
-
-template <int LANES, int PAIRS>
+template <int LANES, int PAIRS, int CSB>
 __global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                     const float *__restrict__ attn, float *__restrict__ out,
-                     int M, int L, int P, int Lq, int64_t value_batch_stride,
-                     int cl /* samples per pair per pass */)
+                     const float *__restrict__ attn, float *__restrict__ out, const FastArgs a)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
+    float4 *wts = reinterpret_cast<float4 *>(smem_raw);
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * a.cl);
 
     const int tid = threadIdx.x;
-    const int LP = L * P;
-    const TileCoord tc = tile_of_block(M, Lq, Cfg::PAIRS);
-    const int cs = M * LANES;  // float4 units between consecutive cells
+    const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
+    const int LP = a.L * a.P;
 
-    load_level_table(lv, shapes, lsi, L);
+    load_level_table(lv, shapes, lsi, a.L);
     __syncthreads();
 
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
-    const bool live = tc.q0 + pl < Lq;
-    const size_t pair = ((size_t)tc.n * Lq + tc.q0 + pl) * M + tc.m;
-    const float4 *vbase =
-        reinterpret_cast<const float4 *>(value + (int64_t)tc.n * value_batch_stride) + tc.m * LANES + lane;
+    const bool live = q0 + pl < a.Lq;
+    const size_t pair = ((size_t)nb * a.Lq + q0 + pl) * a.M + m;
+    const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
+                     (size_t)(m * LANES + lane) * 16;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int lp0 = 0; lp0 < LP; lp0 += cl) {
-        const int n = min(cl, LP - lp0);
+    for (int lp0 = 0; lp0 < LP; lp0 += a.cl) {
+        const int n = min(a.cl, LP - lp0);
+        const unsigned magic_n = n == a.cl ? a.magic_cl : fast_magic_dev(n);
         // ---- phase 1: one thread per sample ----
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
-            const int spl = i / n;
+            const int spl = fast_div(i, magic_n);
             const int lp = lp0 + (i - spl * n);
-            Rec r = empty_rec();
-            if (tc.q0 + spl < Lq) {
-                const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
+            SampleMeta mt = empty_meta();
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + spl < a.Lq) {
+                const size_t si = (((size_t)nb * a.Lq + q0 + spl) * a.M + m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
-                const int l = lp / P;
-                r = make_rec(make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]), __ldg(attn + si));
+                const float at = __ldg(attn + si);
+                const int l = fast_div(lp, a.magic_P);
+                const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
+                mt = make_meta(s, lv.W[l], a.cell_bytes);
+                const float hx = 1.f - s.lx, hy = 1.f - s.ly;
+                w = make_float4(hy * hx * at, hy * s.lx * at, s.ly * hx * at, s.ly * s.lx * at);
             }
-            rec[i] = r;
+            meta[i] = mt;
+            wts[i] = w;
         }
         __syncthreads();
         // ---- phase 2: gather ----
         if (live) {
-            const Rec *my = rec + pl * n;
-            LevelWalker lw(lv, lp0, P, L, cs);
+            const SampleMeta *mm = meta + pl * n;
+            const float4 *ww = wts + pl * n;
 #pragma unroll 4
-            for (int j = 0; j < n; ++j) {
-                const Rec r = my[j];
-                int o0;
-                float4 v0, v1, v2, v3;
-                gather4(r, vbase, cs, lw.wcs, o0, v0, v1, v2, v3);
-                const float hx = 1.f - r.lx, hy = 1.f - r.ly;
-                const float ahy = r.a * hy, aly = r.a * r.ly;
-                fma4(acc, ahy * hx, v0);
-                fma4(acc, ahy * r.lx, v1);
-                fma4(acc, aly * hx, v2);
-                fma4(acc, aly * r.lx, v3);
-                lw.next(lv);
-            }
+            for (int j = 0; j < n; ++j) gather_fma<CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
         }
-        if (lp0 + cl < LP) __syncthreads();  // records are reused by the next pass
+        if (lp0 + a.cl < LP) __syncthreads();  // staging buffers are reused by the next pass
     }
     if (live) reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
 }
 
 // SCATTER == false: grad_sampling_loc / grad_attn_weight only (deterministic mode computes
 // grad_value separately, msda_deterministic.cu)
-template <int LANES, int PAIRS, bool SCATTER>
+template <int LANES, int PAIRS, int CSB, bool SCATTER>
 __global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                      const float *__restrict__ attn, const float *__restrict__ grad_out,
                      float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                     float *__restrict__ grad_attn,
-                     int S, int M, int L, int P, int Lq,
-                     int64_t value_batch_stride, int cl)
+                     float *__restrict__ grad_attn, const FastArgs a)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(Rec) * Cfg::PAIRS * cl);  // [rec][SUBS][3]
+    float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * a.cl);
+    float *part = reinterpret_cast<float *>(smem_raw + (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * a.cl);
 
     const int tid = threadIdx.x;
-    const int LP = L * P;
-    const TileCoord tc = tile_of_block(M, Lq, Cfg::PAIRS);
-    const int cs = M * LANES;
+    const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
+    const int LP = a.L * a.P;
 
-    load_level_table(lv, shapes, lsi, L);
+    load_level_table(lv, shapes, lsi, a.L);
     __syncthreads();
 
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
     const int sub = lane >> 2;
-    const bool live = tc.q0 + pl < Lq;
-    const size_t pair = ((size_t)tc.n * Lq + tc.q0 + pl) * M + tc.m;
-    const float4 *vbase =
-        reinterpret_cast<const float4 *>(value + (int64_t)tc.n * value_batch_stride) + tc.m * LANES + lane;
-    float4 *gvbase =
-        reinterpret_cast<float4 *>(grad_value + (int64_t)tc.n * S * M * (LANES * 4)) + tc.m * LANES + lane;
+    const bool live = q0 + pl < a.Lq;
+    const size_t pair = ((size_t)nb * a.Lq + q0 + pl) * a.M + m;
+    const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
+                     (size_t)(m * LANES + lane) * 16;
+    char *gp0 = reinterpret_cast<char *>(grad_value) + ((size_t)nb * a.S * a.cell_bytes) + (size_t)(m * LANES + lane) * 16;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
 
-    for (int lp0 = 0; lp0 < LP; lp0 += cl) {
-        const int n = min(cl, LP - lp0);
+    for (int lp0 = 0; lp0 < LP; lp0 += a.cl) {
+        const int n = min(a.cl, LP - lp0);
+        const unsigned magic_n = n == a.cl ? a.magic_cl : fast_magic_dev(n);
         // ---- phase 1: one thread per sample ----
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
-            const int spl = i / n;
+            const int spl = fast_div(i, magic_n);
             const int lp = lp0 + (i - spl * n);
-            Rec r = empty_rec();
-            if (tc.q0 + spl < Lq) {
-                const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
+            SampleMeta mt = empty_meta();
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + spl < a.Lq) {
+                const size_t si = (((size_t)nb * a.Lq + q0 + spl) * a.M + m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
-                const int l = lp / P;
-                r = make_rec(make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]), __ldg(attn + si));
+                const int l = fast_div(lp, a.magic_P);
+                const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
+                mt = make_meta(s, lv.W[l], a.cell_bytes);
+                f = make_float4(s.lx, s.ly, __ldg(attn + si), 0.f);
             }
-            rec[i] = r;
+            meta[i] = mt;
+            frac[i] = f;
         }
         __syncthreads();
         // ---- phase 2: gather + scatter; every thread runs it (full-mask shuffles) ----
         {
-            const Rec *my = rec + pl * n;
+            const SampleMeta *mm = meta + pl * n;
+            const float4 *ff = frac + pl * n;
             float *mypart = part + (size_t)(pl * n) * (Cfg::SUBS * 3) + sub * 3;
-            LevelWalker lw(lv, lp0, P, L, cs);
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
-                const Rec r = my[j];
-                int o0;
-                float4 v0, v1, v2, v3;
-                gather4(r, vbase, cs, lw.wcs, o0, v0, v1, v2, v3);
-                const float lx = r.lx, ly = r.ly, a = r.a;
-                const float hx = 1.f - lx, hy = 1.f - ly;
-                const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
-                if (SCATTER) {
-                    // grad_value: w_k * A * G  (vector reductions, one per corner per lane)
-                    const unsigned mask = r.pk >> 28;
-                    const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-                    if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gvbase + o0), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
-                    if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gvbase + o0 + cs), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
-                    if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gvbase + o0 + lw.wcs), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
-                    if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gvbase + o0 + lw.wcs + cs), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
-                }
-                // per-sample scalars: <G,val>, <G,dval/dx>, <G,dval/dy> over this lane's channels
-                float4 val, dxv, dyv;
-                val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-                val.y = w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-                val.z = w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-                val.w = w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
-                dxv.x = hy * (v1.x - v0.x) + ly * (v3.x - v2.x);
-                dxv.y = hy * (v1.y - v0.y) + ly * (v3.y - v2.y);
-                dxv.z = hy * (v1.z - v0.z) + ly * (v3.z - v2.z);
-                dxv.w = hy * (v1.w - v0.w) + ly * (v3.w - v2.w);
-                dyv.x = hx * (v2.x - v0.x) + lx * (v3.x - v1.x);
-                dyv.y = hx * (v2.y - v0.y) + lx * (v3.y - v1.y);
-                dyv.z = hx * (v2.z - v0.z) + lx * (v3.z - v1.z);
-                dyv.w = hx * (v2.w - v0.w) + lx * (v3.w - v1.w);
-                float pa = dot4(g, val), px = dot4(g, dxv), py = dot4(g, dyv);
-                pa += __shfl_xor_sync(0xffffffffu, pa, 1);
-                px += __shfl_xor_sync(0xffffffffu, px, 1);
-                py += __shfl_xor_sync(0xffffffffu, py, 1);
-                pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-                px += __shfl_xor_sync(0xffffffffu, px, 2);
-                py += __shfl_xor_sync(0xffffffffu, py, 2);
+                const float4 f = ff[j];
+                const float4 ga = make_float4(g.x * f.z, g.y * f.z, g.z * f.z, g.w * f.z);
+                float pa = 0.f, px = 0.f, py = 0.f;
+                gather_scatter<CSB, SCATTER>(mm[j], f.x, f.y, ga, g, p0, gp0, a.cell_bytes, pa, px, py);
+                subgroup_sum3(pa, px, py);
                 if ((lane & 3) == 0) {
                     float *dst = mypart + j * (Cfg::SUBS * 3);
                     dst[0] = pa; dst[1] = px; dst[2] = py;
                 }
-                lw.next(lv);
             }
         }
         __syncthreads();
         // ---- phase 3: one thread per sample finishes grad_attn / grad_loc ----
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
-            const int spl = i / n;
+            const int spl = fast_div(i, magic_n);
             const int lp = lp0 + (i - spl * n);
-            if (tc.q0 + spl < Lq) {
+            if (q0 + spl < a.Lq) {
                 const float *p = part + (size_t)i * (Cfg::SUBS * 3);
                 float pa = 0.f, px = 0.f, py = 0.f;
 #pragma unroll
                 for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
-                const float a = rec[i].a;
-                const int l = lp / P;
-                const size_t si = (((size_t)tc.n * Lq + tc.q0 + spl) * M + tc.m) * LP + lp;
+                const float at = frac[i].z;
+                const int l = fast_div(lp, a.magic_P);
+                const size_t si = (((size_t)nb * a.Lq + q0 + spl) * a.M + m) * LP + lp;
                 grad_attn[si] = pa;
                 reinterpret_cast<float2 *>(grad_loc)[si] =
-                    make_float2((float)lv.W[l] * a * px, (float)lv.H[l] * a * py);
+                    make_float2((float)lv.W[l] * at * px, (float)lv.H[l] * at * py);
             }
         }
-        if (lp0 + cl < LP) __syncthreads();
+        if (lp0 + a.cl < LP) __syncthreads();
     }
 }
 
@@ -253,14 +208,30 @@ bool fast_path_ok(const OpDims &d)
     if (d.D % 16 != 0 || d.D > 128) return false;
     if (d.L > kMaxLevels) return false;
     if (d.value_batch_stride % 4 != 0) return false;
-    // in-kernel 32-bit indices: float4 cell offsets, pair and sample counters
-    if ((int64_t)d.S * d.M * (d.D / 4) >= (int64_t)INT32_MAX) return false;
-    if ((int64_t)d.S >= (int64_t)kRecBias - 65536) return false;  // packed cell index (Rec::pk)
-    if ((int64_t)d.N * d.Lq * d.M >= (int64_t)INT32_MAX / 64) return false;
+    // 28-bit row stride / 31-bit cell offsets in bytes (SampleMeta)
+    if ((int64_t)d.S * d.M * d.D * 4 >= ((int64_t)1 << 28)) return false;
+    // grid dimensions (y: query tiles, z: batch) and the 24-bit fast_div range
+    if (d.N > 65535 || (d.Lq + 7) / 8 > 65535) return false;
+    if ((int64_t)d.L * d.P >= 4096) return false;
     return true;
 }
 
-int g_pairs_d48 = 16;  // tile length for LANES == 12 (msda_set_tuning("pairs_d48", 8|16|32))
+int g_pairs_d48 = 16;  // queries per CTA tile for LANES == 12 (msda_set_tuning("pairs_d48", 8|16|32))
+
+template <int LANES, int PAIRS>
+static FastArgs make_fast_args(const OpDims &d)
+{
+    using Cfg = FastCfg<LANES, PAIRS>;
+    const int LP = d.L * d.P;
+    FastArgs a;
+    a.M = d.M; a.L = d.L; a.P = d.P; a.Lq = d.Lq; a.S = d.S;
+    a.cell_bytes = d.M * d.D * 4;
+    a.cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
+    a.magic_cl = fast_magic(a.cl);
+    a.magic_P = fast_magic(d.P);
+    a.value_batch_stride = d.value_batch_stride;
+    return a;
+}
 
 template <int LANES, int PAIRS>
 static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
@@ -268,12 +239,14 @@ static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, co
                                    const OpDims &d, cudaStream_t stream)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
-    const int LP = d.L * d.P;
-    const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
-    const int grid = d.N * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = sizeof(Rec) * Cfg::PAIRS * cl;
-    msda_fwd_fast_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
-        value, shapes, lsi, loc, attn, out, d.M, d.L, d.P, d.Lq, d.value_batch_stride, cl);
+    const FastArgs a = make_fast_args<LANES, PAIRS>(d);
+    const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
+    const size_t smem = (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * a.cl;
+    if (LANES == 12 && d.M == 8)  // Snipper: cell stride 1536 B becomes an immediate offset
+        msda_fwd_fast_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(
+            value, shapes, lsi, loc, attn, out, a);
+    else
+        msda_fwd_fast_kernel<LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
     return cudaGetLastError();
 }
 
@@ -284,13 +257,15 @@ static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, co
                                    const OpDims &d, cudaStream_t stream)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
-    const int LP = d.L * d.P;
-    const int cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
-    const int grid = d.N * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = (sizeof(Rec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * cl;
-    msda_bwd_fast_kernel<LANES, PAIRS, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
-        value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d.S, d.M, d.L,
-        d.P, d.Lq, d.value_batch_stride, cl);
+    const FastArgs a = make_fast_args<LANES, PAIRS>(d);
+    const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
+    const size_t smem = (sizeof(float4) + sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * a.cl;
+    if (LANES == 12 && d.M == 8)
+        msda_bwd_fast_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0), SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
+            value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
+    else
+        msda_bwd_fast_kernel<LANES, PAIRS, 0, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
+            value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
     return cudaGetLastError();
 }
 

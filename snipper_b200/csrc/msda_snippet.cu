@@ -15,15 +15,15 @@
 // phase 1 = one thread per sample (here it also does the softmax and the offset normalisation),
 // phase 2 = lanes gather 128-bit channel chunks; backward adds vector reductions into
 // grad_value, 4-lane shuffles for the per-sample scalars and the softmax backward in phase 3.
-#include "msda_common.cuh"
+#include "msda_fast.cuh"
 #include "msda_internal.h"
 
 namespace msda {
 
 constexpr int kSnippetMaxLP = 32;
 
-// A CTA owns PAIRS consecutive queries of ONE head of one (batch item, query frame): neighbouring
-// encoder queries gather overlapping cells, which then hit in L1 (see msda_percall.cu).
+// grid = (M, query tiles, N*T1): a CTA owns PAIRS consecutive queries of ONE head of one
+// (batch item, query frame); neighbouring encoder queries gather overlapping cells (L1 hits).
 template <int LANES, int PAIRS_>
 struct SnipCfg {
     static constexpr int PAIRS = PAIRS_;
@@ -35,19 +35,11 @@ struct SnipCfg {
     static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
-struct SnipTile { int n, t1, q0, m; };
-
-__device__ __forceinline__ SnipTile snippet_tile_of_block(int M, int Lq, int T1, int pairs)
-{
-    const int tiles = (Lq + pairs - 1) / pairs;
-    int b = blockIdx.x;
-    SnipTile t;
-    t.m = b % M; b /= M;
-    t.q0 = (b % tiles) * pairs; b /= tiles;
-    t.t1 = b % T1;
-    t.n = b / T1;
-    return t;
-}
+struct SnipArgs {
+    SnippetDims d;
+    int cell_bytes;            // M * D * 4
+    unsigned magic_LP, magic_P;
+};
 
 __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo, int &hi)
 {
@@ -56,208 +48,176 @@ __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo
     else { lo = 0; hi = T2 - 1; }
 }
 
-// Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each pair is
+// Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each query is
 // done cooperatively through shared memory (one expf per sample), then
-// loc = ref + offset / (W_l, H_l) in the reference's operation order (ms_deform_attn.py:164-165)
-// and the 16-byte record with A = softmax / k.
-template <int THREADS, int PAIRS>
-__device__ __forceinline__ void snippet_phase1(Rec *rec, float *zs, float *es, const LevelTable &lv,
-                                               const SnippetDims &d, const SnipTile &tc, size_t qbase,
-                                               const float *__restrict__ offsets,
+// loc = ref + offset / (W_l, H_l) in the reference's operation order (ms_deform_attn.py:164-165).
+// FWD: second = per-corner weights (bilinear x A).  BWD: second = {lx, ly, A, -}.   A = softmax / k.
+template <int THREADS, int PAIRS, bool FWD>
+__device__ __forceinline__ void snippet_phase1(SampleMeta *meta, float4 *second, float *zs, float *es,
+                                               const LevelTable &lv, const SnipArgs &a, int n, int t1, int q0,
+                                               int m, size_t qbase, const float *__restrict__ offsets,
                                                const float *__restrict__ logits,
                                                const float *__restrict__ ref, float inv_k)
 {
+    const SnippetDims &d = a.d;
     const int tid = threadIdx.x;
     const int LP = d.L * d.P;
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
-        const int spl = i / LP;
-        const int q = tc.q0 + spl;
-        zs[i] = q < d.Lq ? __ldg(logits + ((qbase + q) * d.M + tc.m) * LP + (i - spl * LP)) : 0.f;
+        const int spl = fast_div(i, a.magic_LP);
+        const int q = q0 + spl;
+        zs[i] = q < d.Lq ? __ldg(logits + ((qbase + q) * d.M + m) * LP + (i - spl * LP)) : 0.f;
     }
     __syncthreads();
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
-        const float *z = zs + (i / LP) * LP;
+        const float *z = zs + fast_div(i, a.magic_LP) * LP;
         float mx = z[0];
         for (int j = 1; j < LP; ++j) mx = fmaxf(mx, z[j]);
         es[i] = expf(zs[i] - mx);
     }
     __syncthreads();
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
-        const int spl = i / LP;
+        const int spl = fast_div(i, a.magic_LP);
         const int lp = i - spl * LP;
-        const int q = tc.q0 + spl;
-        Rec r = empty_rec();
+        const int q = q0 + spl;
+        SampleMeta mt = empty_meta();
+        float4 sec = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < d.Lq) {
             const float *e = es + spl * LP;
             float sum = 0.f;
             for (int j = 0; j < LP; ++j) sum += e[j];
-            const float a = es[i] / sum * inv_k;
-            const size_t sp = (qbase + q) * d.M + tc.m;
-            const int l = lp / d.P;
+            const float at = es[i] / sum * inv_k;
+            const size_t sp = (qbase + q) * d.M + m;
+            const int l = fast_div(lp, a.magic_P);
             const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
-            const float *rp = ref + tc.n * d.ref_stride_n + tc.t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+            const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
             const float u = __ldg(rp) + o.x / (float)lv.W[l];
             const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
-            r = make_rec(make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]), a);
+            const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
+            mt = make_meta(s, lv.W[l], a.cell_bytes);
+            if (FWD) {
+                const float hx = 1.f - s.lx, hy = 1.f - s.ly;
+                sec = make_float4(hy * hx * at, hy * s.lx * at, s.ly * hx * at, s.ly * s.lx * at);
+            } else {
+                sec = make_float4(s.lx, s.ly, at, 0.f);
+            }
         }
-        rec[i] = r;
+        meta[i] = mt;
+        second[i] = sec;
     }
     __syncthreads();
 }
 
-template <int LANES, int PAIRS>
+template <int LANES, int PAIRS, int CSB>
 __global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::FWD_MIN_BLOCKS)
 msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
-                        float *__restrict__ out, SnippetDims d)
+                        float *__restrict__ out, const SnipArgs a)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
+    const SnippetDims &d = a.d;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
-    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
-    float *zs = reinterpret_cast<float *>(smem_raw + sizeof(Rec) * Cfg::PAIRS * LP);
+    float4 *wts = reinterpret_cast<float4 *>(smem_raw);
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * LP);
+    float *zs = reinterpret_cast<float *>(smem_raw + (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * LP);
     float *es = zs + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
-    const SnipTile tc = snippet_tile_of_block(d.M, d.Lq, d.T1, Cfg::PAIRS);
-    const int cs = d.M * LANES;
+    const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS;
+    const int n = blockIdx.z / d.T1, t1 = blockIdx.z - n * d.T1;
     int lo, hi;
-    frame_range(tc.t1, d.n_frame, d.T2, lo, hi);
+    frame_range(t1, d.n_frame, d.T2, lo, hi);
     const int nf = hi - lo + 1;
-    const size_t qbase = ((size_t)tc.n * d.T1 + tc.t1) * d.Lq;  // first query row of this (n, t1)
+    const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;  // first query row of this (n, t1)
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
-    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, d, tc, qbase, offsets, logits, ref, 1.f / (float)nf);
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS, true>(meta, wts, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits,
+                                                  ref, 1.f / (float)nf);
 
     // ---- phase 2: gather from every neighbour frame ----
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
-    if (tc.q0 + pl >= d.Lq) return;
-    const size_t pair = (qbase + tc.q0 + pl) * d.M + tc.m;
-    const float4 *vframe = reinterpret_cast<const float4 *>(value + tc.n * d.value_stride_n + lo * d.value_stride_t) +
-                           tc.m * LANES + lane;
-    const int64_t fstride = d.value_stride_t / 4;  // float4 units
-    const Rec *my = rec + pl * LP;
+    if (q0 + pl >= d.Lq) return;
+    const size_t pair = (qbase + q0 + pl) * d.M + m;
+    const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
+                     (size_t)(m * LANES + lane) * 16;
+    const int64_t fstride = d.value_stride_t * 4;  // bytes between frames
+    const SampleMeta *mm = meta + pl * LP;
+    const float4 *ww = wts + pl * LP;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    LevelWalker lw(lv, 0, d.P, d.L, cs);
-#pragma unroll 2
-    for (int j = 0; j < LP; ++j) {
-        const Rec r = my[j];
-        const float hx = 1.f - r.lx, hy = 1.f - r.ly;
-        const float ahy = r.a * hy, aly = r.a * r.ly;
-        const float w0 = ahy * hx, w1 = ahy * r.lx, w2 = aly * hx, w3 = aly * r.lx;
-        const float4 *vb = vframe;
-        for (int f = 0; f < nf; ++f, vb += fstride) {
-            int o0;
-            float4 v0, v1, v2, v3;
-            gather4(r, vb, cs, lw.wcs, o0, v0, v1, v2, v3);
-            fma4(acc, w0, v0);
-            fma4(acc, w1, v1);
-            fma4(acc, w2, v2);
-            fma4(acc, w3, v3);
-        }
-        lw.next(lv);
-    }
+    for (int j = 0; j < LP; ++j) gather_fma_frames<CSB>(acc, mm[j], ww[j], pf, fstride, nf, a.cell_bytes);
     reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
 }
 
-template <int LANES, int PAIRS>
+template <int LANES, int PAIRS, int CSB>
 __global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS)
 msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
                         const float *__restrict__ grad_out, float *__restrict__ grad_value,
                         float *__restrict__ grad_offsets, float *__restrict__ grad_logits,
-                        SnippetDims d)
+                        const SnipArgs a)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
+    const SnippetDims &d = a.d;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
-    Rec *rec = reinterpret_cast<Rec *>(smem_raw);
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(Rec) * Cfg::PAIRS * LP);  // [rec][SUBS][3]
-    float *zs = part;                       // phase-1 scratch aliases `part` (SUBS*3 >= 2 floats per record)
+    float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * LP);
+    float *part = reinterpret_cast<float *>(smem_raw + (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * LP);
+    float *zs = part;  // phase-1 scratch aliases `part` ([rec][SUBS][3] >= 2 floats per record)
     float *es = part + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
-    const SnipTile tc = snippet_tile_of_block(d.M, d.Lq, d.T1, Cfg::PAIRS);
-    const int cs = d.M * LANES;
+    const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS;
+    const int n = blockIdx.z / d.T1, t1 = blockIdx.z - n * d.T1;
     int lo, hi;
-    frame_range(tc.t1, d.n_frame, d.T2, lo, hi);
+    frame_range(t1, d.n_frame, d.T2, lo, hi);
     const int nf = hi - lo + 1;
-    const size_t qbase = ((size_t)tc.n * d.T1 + tc.t1) * d.Lq;
+    const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
-    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, d, tc, qbase, offsets, logits, ref, 1.f / (float)nf);
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS, false>(meta, frac, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits,
+                                                   ref, 1.f / (float)nf);
 
     // ---- phase 2: every thread participates (full-mask shuffles) ----
     {
         const int pl = tid / LANES;
         const int lane = tid - pl * LANES;
         const int sub = lane >> 2;
-        const bool live = tc.q0 + pl < d.Lq;
-        const size_t pair = (qbase + tc.q0 + pl) * d.M + tc.m;
-        const float4 *vframe =
-            reinterpret_cast<const float4 *>(value + tc.n * d.value_stride_n + lo * d.value_stride_t) +
-            tc.m * LANES + lane;
-        float4 *gvframe =
-            reinterpret_cast<float4 *>(grad_value + ((int64_t)tc.n * d.T2 + lo) * d.S * d.M * (LANES * 4)) +
-            tc.m * LANES + lane;
+        const bool live = q0 + pl < d.Lq;
+        const size_t pair = (qbase + q0 + pl) * d.M + m;
+        const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
+                         (size_t)(m * LANES + lane) * 16;
+        char *gpf = reinterpret_cast<char *>(grad_value) + ((size_t)n * d.T2 + lo) * d.S * a.cell_bytes +
+                    (size_t)(m * LANES + lane) * 16;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
-        const int64_t fstride = d.value_stride_t / 4;
-        const int64_t gfstride = (int64_t)d.S * d.M * LANES;
-        const Rec *my = rec + pl * LP;
+        const int64_t fstride = d.value_stride_t * 4;
+        const int64_t gfstride = (int64_t)d.S * a.cell_bytes;
+        const SampleMeta *mm = meta + pl * LP;
+        const float4 *ff = frac + pl * LP;
         float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
-        LevelWalker lw(lv, 0, d.P, d.L, cs);
         for (int j = 0; j < LP; ++j) {
-            const Rec r = my[j];
-            const unsigned mask = r.pk >> 28;
-            const float lx = r.lx, ly = r.ly, a = r.a;
-            const float hx = 1.f - lx, hy = 1.f - ly;
-            const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
-            const float4 ga = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+            const SampleMeta mt = mm[j];
+            const float4 f = ff[j];
+            const float4 ga = make_float4(g.x * f.z, g.y * f.z, g.z * f.z, g.w * f.z);
             float pa = 0.f, px = 0.f, py = 0.f;
-            const float4 *vb = vframe;
-            float4 *gvb = gvframe;
-            for (int f = 0; f < nf; ++f, vb += fstride, gvb += gfstride) {
-                int o0;
-                float4 v0, v1, v2, v3;
-                gather4(r, vb, cs, lw.wcs, o0, v0, v1, v2, v3);
-                if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gvb + o0), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
-                if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gvb + o0 + cs), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
-                if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gvb + o0 + lw.wcs), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
-                if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gvb + o0 + lw.wcs + cs), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
-                float4 val, dxv, dyv;
-                val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-                val.y = w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-                val.z = w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-                val.w = w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
-                dxv.x = hy * (v1.x - v0.x) + ly * (v3.x - v2.x);
-                dxv.y = hy * (v1.y - v0.y) + ly * (v3.y - v2.y);
-                dxv.z = hy * (v1.z - v0.z) + ly * (v3.z - v2.z);
-                dxv.w = hy * (v1.w - v0.w) + ly * (v3.w - v2.w);
-                dyv.x = hx * (v2.x - v0.x) + lx * (v3.x - v1.x);
-                dyv.y = hx * (v2.y - v0.y) + lx * (v3.y - v1.y);
-                dyv.z = hx * (v2.z - v0.z) + lx * (v3.z - v1.z);
-                dyv.w = hx * (v2.w - v0.w) + lx * (v3.w - v1.w);
-                pa += dot4(g, val); px += dot4(g, dxv); py += dot4(g, dyv);
-            }
-            pa += __shfl_xor_sync(0xffffffffu, pa, 1);
-            px += __shfl_xor_sync(0xffffffffu, px, 1);
-            py += __shfl_xor_sync(0xffffffffu, py, 1);
-            pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-            px += __shfl_xor_sync(0xffffffffu, px, 2);
-            py += __shfl_xor_sync(0xffffffffu, py, 2);
+            const char *p0 = pf;
+            char *gp0 = gpf;
+            for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
+                gather_scatter<CSB, true>(mt, f.x, f.y, ga, g, p0, gp0, a.cell_bytes, pa, px, py);
+            subgroup_sum3(pa, px, py);
+            // zs/es alias `part`: all phase-1 reads finished at the barrier that ends phase 1
             if ((lane & 3) == 0) {
                 float *dst = mypart + j * (Cfg::SUBS * 3);
                 dst[0] = pa; dst[1] = px; dst[2] = py;
             }
-            lw.next(lv);
         }
     }
     __syncthreads();
@@ -272,25 +232,25 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
 #pragma unroll
         for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
         pa_i[it] = pa;
-        const float a = rec[i].a;
-        const int spl = i / LP;
-        if (tc.q0 + spl < d.Lq) {
+        const float at = frac[i].z;
+        const int spl = fast_div(i, a.magic_LP);
+        if (q0 + spl < d.Lq) {
             // loc = ref + off/(W,H) and x = loc*W - 0.5  =>  dx/doff_x = 1: the W factor of the
             // per-call grad_loc (W*A*px) cancels against the 1/W of the normalisation.
-            const size_t si = ((qbase + tc.q0 + spl) * d.M + tc.m) * LP + (i - spl * LP);
-            reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(a * px, a * py);
+            const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
+            reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(at * px, at * py);
         }
-        part[(size_t)i * (Cfg::SUBS * 3)] = pa * a;  // own slot only
+        part[(size_t)i * (Cfg::SUBS * 3)] = pa * at;  // own slot only
     }
     __syncthreads();
     it = 0;
     for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS, ++it) {
-        const int spl = i / LP;
-        if (tc.q0 + spl < d.Lq) {
+        const int spl = fast_div(i, a.magic_LP);
+        if (q0 + spl < d.Lq) {
             float dot = 0.f;
             for (int j = 0; j < LP; ++j) dot += part[(size_t)(spl * LP + j) * (Cfg::SUBS * 3)];
-            const size_t si = ((qbase + tc.q0 + spl) * d.M + tc.m) * LP + (i - spl * LP);
-            grad_logits[si] = rec[i].a * (pa_i[it] - (float)nf * dot);
+            const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
+            grad_logits[si] = frac[i].z * (pa_i[it] - (float)nf * dot);
         }
     }
 }
@@ -300,13 +260,22 @@ bool snippet_ok(const SnippetDims &d)
     if (d.D % 16 != 0 || d.D > 128) return false;
     if (d.L > kMaxLevels || d.L * d.P > kSnippetMaxLP) return false;
     if (d.value_stride_n % 4 != 0 || d.value_stride_t % 4 != 0) return false;
-    if ((int64_t)d.S * d.M * (d.D / 4) >= (int64_t)INT32_MAX) return false;
-    if ((int64_t)d.S >= (int64_t)kRecBias - 65536) return false;  // packed cell index (Rec::pk)
-    if ((int64_t)d.N * d.T1 * d.Lq * d.M >= (int64_t)INT32_MAX / 64) return false;
+    if ((int64_t)d.S * d.M * d.D * 4 >= ((int64_t)1 << 28)) return false;  // SampleMeta bit budget
+    if ((int64_t)d.N * d.T1 > 65535 || (d.Lq + 7) / 8 > 65535) return false;
     return true;
 }
 
 int g_snip_pairs_d48 = 16;  // msda_set_tuning("snip_pairs_d48", 8|16|32)
+
+static SnipArgs make_snip_args(const SnippetDims &d)
+{
+    SnipArgs a;
+    a.d = d;
+    a.cell_bytes = d.M * d.D * 4;
+    a.magic_LP = fast_magic(d.L * d.P);
+    a.magic_P = fast_magic(d.P);
+    return a;
+}
 
 template <int LANES, int PAIRS>
 static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, const int64_t *lsi,
@@ -314,10 +283,32 @@ static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, co
                                    float *out, const SnippetDims &d, cudaStream_t stream)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
-    const int grid = d.N * d.T1 * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = (sizeof(Rec) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
-    msda_snippet_fwd_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets,
-                                                                               logits, ref, out, d);
+    const SnipArgs a = make_snip_args(d);
+    const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
+    const size_t smem = (sizeof(float4) + sizeof(SampleMeta) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
+    if (LANES == 12 && d.M == 8)
+        msda_snippet_fwd_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(
+            value, shapes, lsi, offsets, logits, ref, out, a);
+    else
+        msda_snippet_fwd_kernel<LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets,
+                                                                                    logits, ref, out, a);
+    return cudaGetLastError();
+}
+
+template <int LANES, int PAIRS, int CSB>
+static cudaError_t launch_snip_bwd_impl(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                        const float *offsets, const float *logits, const float *ref,
+                                        const float *grad_out, float *grad_value, float *grad_offsets,
+                                        float *grad_logits, const SnippetDims &d, cudaStream_t stream)
+{
+    using Cfg = SnipCfg<LANES, PAIRS>;
+    const SnipArgs a = make_snip_args(d);
+    const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
+    const size_t smem = (sizeof(float4) + sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(msda_snippet_bwd_kernel<LANES, PAIRS, CSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    msda_snippet_bwd_kernel<LANES, PAIRS, CSB><<<grid, Cfg::THREADS, smem, stream>>>(
+        value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, a);
     return cudaGetLastError();
 }
 
@@ -327,14 +318,11 @@ static cudaError_t launch_snip_bwd(const float *value, const int64_t *shapes, co
                                    const float *grad_out, float *grad_value, float *grad_offsets,
                                    float *grad_logits, const SnippetDims &d, cudaStream_t stream)
 {
-    using Cfg = SnipCfg<LANES, PAIRS>;
-    const int grid = d.N * d.T1 * ((d.Lq + PAIRS - 1) / PAIRS) * d.M;
-    const size_t smem = (sizeof(Rec) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(msda_snippet_bwd_kernel<LANES, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    msda_snippet_bwd_kernel<LANES, PAIRS><<<grid, Cfg::THREADS, smem, stream>>>(
-        value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d);
-    return cudaGetLastError();
+    if (LANES == 12 && d.M == 8)
+        return launch_snip_bwd_impl<LANES, PAIRS, (LANES == 12 ? 1536 : 0)>(value, shapes, lsi, offsets, logits, ref, grad_out,
+                                                                         grad_value, grad_offsets, grad_logits, d, stream);
+    return launch_snip_bwd_impl<LANES, PAIRS, 0>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value,
+                                                 grad_offsets, grad_logits, d, stream);
 }
 
 #define MSDA_DISPATCH_LANES(D, CALL)                                  \
