@@ -25,9 +25,6 @@ namespace {
 constexpr int kScanBlock = 256;
 constexpr int kScanItems = 8;  // per thread
 constexpr int kScanTile = kScanBlock * kScanItems;
-constexpr int kReduceLanes = 16;        // lanes per destination cell
-constexpr int kReduceCellsPerBlock = 8; // 128 threads
-constexpr int kMaxListInSmem = 192;     // records per cell staged in shared memory
 
 struct __align__(8) CornerRec {
     int id;    // (sample index) * 4 + corner
@@ -35,7 +32,7 @@ struct __align__(8) CornerRec {
 };
 
 struct DetLayout {
-    size_t count, cursor, start, blocksums, records, total;
+    size_t count, cursor, long_cells, start, blocksums, records, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -49,6 +46,7 @@ DetLayout det_layout(const OpDims &d)
     size_t off = 0;
     l.count = off; off = align256(off + sizeof(int) * cells);
     l.cursor = off; off = align256(off + sizeof(int) * cells);
+    l.long_cells = off; off = align256(off + sizeof(int) * (cells + 1));  // queue of over-long lists
     l.start = off; off = align256(off + sizeof(int) * (cells + 1));
     l.blocksums = off; off = align256(off + sizeof(int) * (nblocks + 1));
     l.records = off; off = align256(off + sizeof(CornerRec) * corners);
@@ -161,47 +159,151 @@ scan_add_kernel(int *__restrict__ out, const int *__restrict__ blocksums, int64_
 }
 
 // ---- pass 2: per-cell ordered sum ----
-__global__ void __launch_bounds__(kReduceLanes * kReduceCellsPerBlock)
+// Every destination cell (n, s, m) owns a list of (corner id, weight) records in arbitrary order.
+// The list is put into a canonical order -- ascending corner id, by a rank sort in shared memory --
+// and summed in that order with a fixed reduction shape, so the bits of grad_value do not depend
+// on how the atomics of pass 1 interleaved.
+//
+//   det_reduce_kernel       one WARP per cell, lists up to kWarpList records; longer lists are
+//                           queued (their cell index appended to `long_cells`)
+//   det_reduce_long_kernel  one CTA per queued cell, lists up to kBlockList records in dynamic
+//                           shared memory; beyond that a (slow, still deterministic) selection
+//                           straight from global memory
+//
+// Summation shape: the D channels are owned by D/4 float4 lanes (scalar lanes when D % 4 != 0);
+// when 2 * D/4 <= 32 two lane groups take the even / odd positions of the ordered list and are
+// combined at the end -- a fixed tree, hence reproducible.
+struct ListSmem {
+    int *id;         // corner id (sort key)
+    int *row;        // pair index = id / (4 * LP): row of grad_out
+    float *w;
+    unsigned short *order;  // order[rank] = position in the unsorted list
+};
+
+__device__ __forceinline__ void rank_sort(const ListSmem &l, int cnt, int tid, int nthreads)
+{
+    for (int i = tid; i < cnt; i += nthreads) {
+        const int key = l.id[i];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) rank += l.id[j] < key;  // ids are unique
+        l.order[rank] = (unsigned short)i;
+    }
+}
+
+// Ordered sum of one cell by one warp.  Returns through `dst` (global).
+__device__ __forceinline__ void ordered_sum_warp(const ListSmem &l, int cnt, const float *__restrict__ grad_out,
+                                                 float *__restrict__ dst, int D, int lane, bool accumulate)
+{
+    const int q4 = D >> 2;
+    if ((D & 3) == 0 && q4 <= 16) {
+        // two interleaved partial sums: lanes [0,q4) take even list positions, [q4,2*q4) odd ones
+        const int half = lane / q4, c4 = lane - half * q4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (half < 2) {
+            for (int t = half; t < cnt; t += 2) {
+                const int i = l.order[t];
+                const float4 g = __ldg(reinterpret_cast<const float4 *>(grad_out + (int64_t)l.row[i] * D) + c4);
+                fma4(acc, l.w[i], g);
+            }
+        }
+        // lane c4 (first group) adds the second group's partial sum
+        const int src = lane + q4 < 32 ? lane + q4 : lane;
+        const float ox = __shfl_sync(0xffffffffu, acc.x, src), oy = __shfl_sync(0xffffffffu, acc.y, src);
+        const float oz = __shfl_sync(0xffffffffu, acc.z, src), ow = __shfl_sync(0xffffffffu, acc.w, src);
+        if (half == 0) {
+            float4 r = make_float4(acc.x + ox, acc.y + oy, acc.z + oz, acc.w + ow);
+            float4 *d4 = reinterpret_cast<float4 *>(dst) + c4;
+            if (accumulate) { const float4 o = *d4; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+            *d4 = r;
+        }
+    } else {
+        for (int c = lane; c < D; c += 32) {
+            float acc = 0.f;
+            for (int t = 0; t < cnt; ++t) {
+                const int i = l.order[t];
+                acc = fmaf(l.w[i], __ldg(grad_out + (int64_t)l.row[i] * D + c), acc);
+            }
+            dst[c] = accumulate ? dst[c] + acc : acc;
+        }
+    }
+}
+
+constexpr int kWarpList = 640;         // records per warp-owned list (14 B each in smem)
+constexpr int kReduceWarps = 4;
+constexpr int kBlockList = 8192;       // records per CTA-owned list
+constexpr int kLongThreads = 256;
+
+__global__ void __launch_bounds__(32 * kReduceWarps)
 det_reduce_kernel(const float *__restrict__ grad_out, const int *__restrict__ start,
                   const CornerRec *__restrict__ records, float *__restrict__ grad_value,
+                  int *__restrict__ long_cells /* [0] = count, then cell indices */,
                   int D, int LP, int64_t cells, int accumulate)
 {
-    __shared__ CornerRec raw[kReduceCellsPerBlock][kMaxListInSmem];
-    __shared__ CornerRec sorted[kReduceCellsPerBlock][kMaxListInSmem];
-    const int g = threadIdx.x / kReduceLanes;
-    const int lane = threadIdx.x % kReduceLanes;
-    const unsigned gmask = 0xffffu << ((threadIdx.x & 31) / kReduceLanes * kReduceLanes);
-    for (int64_t cell0 = (int64_t)blockIdx.x * kReduceCellsPerBlock; cell0 < cells;
-         cell0 += (int64_t)gridDim.x * kReduceCellsPerBlock) {
-        const int64_t cell = cell0 + g;
-        const bool live = cell < cells;
-        const int lo = live ? start[cell] : 0;
-        const int cnt = live ? start[cell + 1] - lo : 0;
+    __shared__ int s_id[kReduceWarps][kWarpList];
+    __shared__ int s_row[kReduceWarps][kWarpList];
+    __shared__ float s_w[kReduceWarps][kWarpList];
+    __shared__ unsigned short s_order[kReduceWarps][kWarpList];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ListSmem l{s_id[wid], s_row[wid], s_w[wid], s_order[wid]};
+    const int lp4 = 4 * LP;
+    for (int64_t cell = (int64_t)blockIdx.x * kReduceWarps + wid; cell < cells;
+         cell += (int64_t)gridDim.x * kReduceWarps) {
+        const int lo = start[cell];
+        const int cnt = start[cell + 1] - lo;
         float *dst = grad_value + cell * D;
-        if (cnt <= kMaxListInSmem) {
-            for (int i = lane; i < cnt; i += kReduceLanes) raw[g][i] = records[lo + i];
-            __syncwarp(gmask);
-            // rank sort by id (ids are unique): canonical order independent of the fill order
-            for (int i = lane; i < cnt; i += kReduceLanes) {
-                const CornerRec r = raw[g][i];
-                int rank = 0;
-                for (int j = 0; j < cnt; ++j) rank += raw[g][j].id < r.id;
-                sorted[g][rank] = r;
+        if (cnt > kWarpList) {
+            if (lane == 0) long_cells[1 + atomicAdd(long_cells, 1)] = (int)cell;
+            continue;
+        }
+        for (int i = lane; i < cnt; i += 32) {
+            const CornerRec r = records[lo + i];
+            l.id[i] = r.id;
+            l.row[i] = r.id / lp4;
+            l.w[i] = r.w;
+        }
+        __syncwarp();
+        rank_sort(l, cnt, lane, 32);
+        __syncwarp();
+        ordered_sum_warp(l, cnt, grad_out, dst, D, lane, accumulate != 0);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kLongThreads)
+det_reduce_long_kernel(const float *__restrict__ grad_out, const int *__restrict__ start,
+                       const CornerRec *__restrict__ records, float *__restrict__ grad_value,
+                       const int *__restrict__ long_cells, int D, int LP, int accumulate)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    ListSmem l;
+    l.id = reinterpret_cast<int *>(dyn);
+    l.row = l.id + kBlockList;
+    l.w = reinterpret_cast<float *>(l.row + kBlockList);
+    l.order = reinterpret_cast<unsigned short *>(l.w + kBlockList);
+    const int n_long = long_cells[0];
+    const int lp4 = 4 * LP;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int k = blockIdx.x; k < n_long; k += gridDim.x) {
+        const int64_t cell = long_cells[1 + k];
+        const int lo = start[cell];
+        const int cnt = start[cell + 1] - lo;
+        float *dst = grad_value + cell * D;
+        if (cnt <= kBlockList) {
+            for (int i = tid; i < cnt; i += kLongThreads) {
+                const CornerRec r = records[lo + i];
+                l.id[i] = r.id;
+                l.row[i] = r.id / lp4;
+                l.w[i] = r.w;
             }
-            __syncwarp(gmask);
-            for (int c = lane; c < D; c += kReduceLanes) {
-                float acc = 0.f;
-                for (int t = 0; t < cnt; ++t) {
-                    const CornerRec r = sorted[g][t];
-                    const int64_t pair = (int64_t)(r.id >> 2) / LP;
-                    acc = fmaf(r.w, __ldg(grad_out + pair * D + c), acc);
-                }
-                if (live) dst[c] = accumulate ? dst[c] + acc : acc;
-            }
-            __syncwarp(gmask);
+            __syncthreads();
+            rank_sort(l, cnt, tid, kLongThreads);
+            __syncthreads();
+            // the ordered sum itself is one warp's job (fixed reduction shape, same as the short path)
+            if (wid == 0) ordered_sum_warp(l, cnt, grad_out, dst, D, lane, accumulate != 0);
+            __syncthreads();
         } else {
-            // very long list (pathological pile-up on one cell): selection in id order from global
-            for (int c = lane; c < D; c += kReduceLanes) {
+            // pathological pile-up: selection in id order straight from global memory
+            for (int c = tid; c < D; c += kLongThreads) {
                 float acc = 0.f;
                 int last = -1;
                 for (int t = 0; t < cnt; ++t) {
@@ -212,8 +314,7 @@ det_reduce_kernel(const float *__restrict__ grad_out, const int *__restrict__ st
                         if (r.id > last && r.id < best) { best = r.id; bw = r.w; }
                     }
                     last = best;
-                    const int64_t pair = (int64_t)(best >> 2) / LP;
-                    acc = fmaf(bw, __ldg(grad_out + pair * D + c), acc);
+                    acc = fmaf(bw, __ldg(grad_out + (int64_t)(best / lp4) * D + c), acc);
                 }
                 dst[c] = accumulate ? dst[c] + acc : acc;
             }
@@ -252,7 +353,8 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
     cudaError_t e = launch_backward_no_scatter_f32(value, shapes, lsi, loc, attn, grad_out, grad_loc, grad_attn, d, stream);
     if (e != cudaSuccess) return e;
     if (cells == 0) return cudaSuccess;
-    // count and cursor are adjacent regions: one memset clears both
+    int *long_cells = reinterpret_cast<int *>(ws + lay.long_cells);
+    // count, cursor and the long-list queue are adjacent regions: one memset clears all three
     e = cudaMemsetAsync(count, 0, lay.start - lay.count, stream);
     if (e != cudaSuccess) return e;
     const int sample_blocks = (int)((samples + 255) / 256 < 148 * 32 ? (samples + 255) / 256 : 148 * 32);
@@ -266,9 +368,17 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
     if (samples > 0)
         det_count_fill_kernel<true><<<sample_blocks, 256, 0, stream>>>(shapes, lsi, loc, attn, count, cursor, start,
                                                                      records, d.S, d.M, d.L, d.P, d.Lq, samples);
-    const int64_t rblocks = (cells + kReduceCellsPerBlock - 1) / kReduceCellsPerBlock;
-    det_reduce_kernel<<<(int)(rblocks < 148 * 64 ? rblocks : 148 * 64), kReduceLanes * kReduceCellsPerBlock, 0, stream>>>(
-        grad_out, start, records, grad_value, d.D, d.L * d.P, cells, accumulate ? 1 : 0);
+    const int64_t rblocks = (cells + kReduceWarps - 1) / kReduceWarps;
+    det_reduce_kernel<<<(int)(rblocks < 148 * 32 ? rblocks : 148 * 32), 32 * kReduceWarps, 0, stream>>>(
+        grad_out, start, records, grad_value, long_cells, d.D, d.L * d.P, cells, accumulate ? 1 : 0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // over-long lists (none at Snipper's sizes unless many queries pile onto a coarse level)
+    const size_t long_smem = (size_t)kBlockList * (3 * sizeof(int) + sizeof(unsigned short));
+    e = cudaFuncSetAttribute(det_reduce_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem);
+    if (e != cudaSuccess) return e;
+    det_reduce_long_kernel<<<148, kLongThreads, long_smem, stream>>>(grad_out, start, records, grad_value, long_cells,
+                                                                    d.D, d.L * d.P, accumulate ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -82,6 +82,34 @@ __device__ __forceinline__ void gather_fma(float4 &acc, const SampleMeta mt, con
     }
 }
 
+// Two samples per step: when both have all four corners, the eight gathers are issued before any
+// of the 32 FFMAs so twice as many loads are in flight per warp.
+template <int CSB>
+__device__ __forceinline__ void gather_fma2(float4 &acc, const SampleMeta m0, const float4 w0, const SampleMeta m1,
+                                            const float4 w1, const char *__restrict__ p0, int runtime_csb)
+{
+    const int csb = cell_stride_bytes<CSB>(runtime_csb);
+    if (m0.wm >= kAllCorners && m1.wm >= kAllCorners) {
+        const char *a0 = p0 + (ptrdiff_t)m0.off;
+        const char *a2 = a0 + (m0.wm & 0x0fffffffu);
+        const char *b0 = p0 + (ptrdiff_t)m1.off;
+        const char *b2 = b0 + (m1.wm & 0x0fffffffu);
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(a0));
+        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(a0 + csb));
+        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(a2));
+        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(a2 + csb));
+        const float4 u0 = __ldg(reinterpret_cast<const float4 *>(b0));
+        const float4 u1 = __ldg(reinterpret_cast<const float4 *>(b0 + csb));
+        const float4 u2 = __ldg(reinterpret_cast<const float4 *>(b2));
+        const float4 u3 = __ldg(reinterpret_cast<const float4 *>(b2 + csb));
+        fma4(acc, w0.x, v0); fma4(acc, w0.y, v1); fma4(acc, w0.z, v2); fma4(acc, w0.w, v3);
+        fma4(acc, w1.x, u0); fma4(acc, w1.y, u1); fma4(acc, w1.z, u2); fma4(acc, w1.w, u3);
+    } else {
+        gather_fma<CSB>(acc, m0, w0, p0, runtime_csb);
+        gather_fma<CSB>(acc, m1, w1, p0, runtime_csb);
+    }
+}
+
 // Same, over `nf` consecutive value frames (fused snippet kernel): the sample set-up is shared by all
 // neighbour frames, so the fast/slow decision is taken once and the frame loop is branch-free,
 // which lets the loads of two frames overlap.
@@ -117,62 +145,79 @@ __device__ __forceinline__ void gather_fma_frames(float4 &acc, const SampleMeta 
     }
 }
 
+// Per-sample scalars a backward lane needs, derived once per sample from {lx, ly, A}
+// (outside the neighbour-frame loop of the fused kernel).
+struct BwdWeights {
+    float lx, ly, hx, hy;
+    float w0, w1, w2, w3;      // bilinear corner weights
+    float a0, a1, a2, a3;      // w_k * A  (what is scattered into grad_value, times G)
+};
+
+__device__ __forceinline__ BwdWeights make_bwd_weights(float lx, float ly, float at)
+{
+    BwdWeights b;
+    b.lx = lx; b.ly = ly; b.hx = 1.f - lx; b.hy = 1.f - ly;
+    b.w0 = b.hy * b.hx; b.w1 = b.hy * lx; b.w2 = ly * b.hx; b.w3 = ly * lx;
+    b.a0 = b.w0 * at; b.a1 = b.w1 * at; b.a2 = b.w2 * at; b.a3 = b.w3 * at;
+    return b;
+}
+
 // Backward work of one sample for this lane on one value frame: scatter w_k*A*G into grad_value
 // (vector reductions) and accumulate the three per-sample partial dot products.
+// "Dot first": d_k = <G, V_k> over this lane's 4 channels, then
+//     <G, val>      = sum_k w_k d_k
+//     <G, dval/dx>  = hy (d1 - d0) + ly (d3 - d2)
+//     <G, dval/dy>  = hx (d2 - d0) + lx (d3 - d1)
+// -- 28 FP instructions instead of the 60 of forming val / dval per channel and dotting after.
 template <int CSB, bool SCATTER>
-__device__ __forceinline__ void gather_scatter(const SampleMeta mt, float lx, float ly, const float4 ga,
-                                               const float4 g, const char *__restrict__ p0, char *gp0,
+__device__ __forceinline__ void gather_scatter(const SampleMeta mt, const BwdWeights &b, const float4 g,
+                                               const char *__restrict__ p0, char *gp0,
                                                int runtime_csb, float &pa, float &px, float &py)
 {
     const int csb = cell_stride_bytes<CSB>(runtime_csb);
     const ptrdiff_t o0 = (ptrdiff_t)mt.off;
     const ptrdiff_t o2 = o0 + (mt.wm & 0x0fffffffu);
-    const float hx = 1.f - lx, hy = 1.f - ly;
-    const float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
-    float4 v0, v1, v2, v3;
+    float d0, d1, d2, d3;
     if (mt.wm >= kAllCorners) {
-        v0 = __ldg(reinterpret_cast<const float4 *>(p0 + o0));
-        v1 = __ldg(reinterpret_cast<const float4 *>(p0 + o0 + csb));
-        v2 = __ldg(reinterpret_cast<const float4 *>(p0 + o2));
-        v3 = __ldg(reinterpret_cast<const float4 *>(p0 + o2 + csb));
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p0 + o0));
+        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p0 + o0 + csb));
+        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p0 + o2));
+        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p0 + o2 + csb));
         if (SCATTER) {
-            red_add_v4(reinterpret_cast<float *>(gp0 + o0), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
-            red_add_v4(reinterpret_cast<float *>(gp0 + o0 + csb), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
-            red_add_v4(reinterpret_cast<float *>(gp0 + o2), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
-            red_add_v4(reinterpret_cast<float *>(gp0 + o2 + csb), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+            red_add_v4(reinterpret_cast<float *>(gp0 + o0), b.a0 * g.x, b.a0 * g.y, b.a0 * g.z, b.a0 * g.w);
+            red_add_v4(reinterpret_cast<float *>(gp0 + o0 + csb), b.a1 * g.x, b.a1 * g.y, b.a1 * g.z, b.a1 * g.w);
+            red_add_v4(reinterpret_cast<float *>(gp0 + o2), b.a2 * g.x, b.a2 * g.y, b.a2 * g.z, b.a2 * g.w);
+            red_add_v4(reinterpret_cast<float *>(gp0 + o2 + csb), b.a3 * g.x, b.a3 * g.y, b.a3 * g.z, b.a3 * g.w);
         }
+        d0 = dot4(g, v0); d1 = dot4(g, v1); d2 = dot4(g, v2); d3 = dot4(g, v3);
     } else {
         const unsigned mask = mt.wm >> 28;
         if (mask == 0u) return;  // inactive sample contributes nothing anywhere
-        v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0; v2 = v0; v3 = v0;
-        if (mask & 1u) v0 = __ldg(reinterpret_cast<const float4 *>(p0 + o0));
-        if (mask & 2u) v1 = __ldg(reinterpret_cast<const float4 *>(p0 + o0 + csb));
-        if (mask & 4u) v2 = __ldg(reinterpret_cast<const float4 *>(p0 + o2));
-        if (mask & 8u) v3 = __ldg(reinterpret_cast<const float4 *>(p0 + o2 + csb));
+        d0 = 0.f; d1 = 0.f; d2 = 0.f; d3 = 0.f;
+        if (mask & 1u) d0 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o0)));
+        if (mask & 2u) d1 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o0 + csb)));
+        if (mask & 4u) d2 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o2)));
+        if (mask & 8u) d3 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o2 + csb)));
         if (SCATTER) {
-            if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gp0 + o0), w0 * ga.x, w0 * ga.y, w0 * ga.z, w0 * ga.w);
-            if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gp0 + o0 + csb), w1 * ga.x, w1 * ga.y, w1 * ga.z, w1 * ga.w);
-            if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gp0 + o2), w2 * ga.x, w2 * ga.y, w2 * ga.z, w2 * ga.w);
-            if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gp0 + o2 + csb), w3 * ga.x, w3 * ga.y, w3 * ga.z, w3 * ga.w);
+            if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gp0 + o0), b.a0 * g.x, b.a0 * g.y, b.a0 * g.z, b.a0 * g.w);
+            if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gp0 + o0 + csb), b.a1 * g.x, b.a1 * g.y, b.a1 * g.z, b.a1 * g.w);
+            if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gp0 + o2), b.a2 * g.x, b.a2 * g.y, b.a2 * g.z, b.a2 * g.w);
+            if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gp0 + o2 + csb), b.a3 * g.x, b.a3 * g.y, b.a3 * g.z, b.a3 * g.w);
         }
     }
-    // val = sum w_k v_k ; dval/dx = hy (v1 - v0) + ly (v3 - v2) ; dval/dy = hx (v2 - v0) + lx (v3 - v1)
-    float4 val, dxv, dyv;
-    val.x = w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-    val.y = w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-    val.z = w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-    val.w = w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
-    dxv.x = hy * (v1.x - v0.x) + ly * (v3.x - v2.x);
-    dxv.y = hy * (v1.y - v0.y) + ly * (v3.y - v2.y);
-    dxv.z = hy * (v1.z - v0.z) + ly * (v3.z - v2.z);
-    dxv.w = hy * (v1.w - v0.w) + ly * (v3.w - v2.w);
-    dyv.x = hx * (v2.x - v0.x) + lx * (v3.x - v1.x);
-    dyv.y = hx * (v2.y - v0.y) + lx * (v3.y - v1.y);
-    dyv.z = hx * (v2.z - v0.z) + lx * (v3.z - v1.z);
-    dyv.w = hx * (v2.w - v0.w) + lx * (v3.w - v1.w);
-    pa += dot4(g, val);
-    px += dot4(g, dxv);
-    py += dot4(g, dyv);
+    pa = fmaf(b.w0, d0, fmaf(b.w1, d1, fmaf(b.w2, d2, fmaf(b.w3, d3, pa))));
+    px = fmaf(b.hy, d1 - d0, fmaf(b.ly, d3 - d2, px));
+    py = fmaf(b.hx, d2 - d0, fmaf(b.lx, d3 - d1, py));
+}
+
+// Queries per CTA tile for D = 48.  The tuned default is 16; when that would leave the GPU with
+// fewer than ~3 CTAs per SM (decoder: Lq = 60) halve the tile so twice as many CTAs are in flight
+// -- those launches are latency-bound, not bandwidth-bound.
+inline int pick_pairs_d48(int configured, int Lq, int M, int nz)
+{
+    if (configured != 16) return configured;
+    const long long ctas = (long long)((Lq + 15) / 16) * M * nz;
+    return ctas < 148 * 3 ? 8 : 16;
 }
 
 // sum over the 4 lanes of a shuffle sub-group (full-warp participation required)

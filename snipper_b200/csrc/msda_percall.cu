@@ -37,6 +37,8 @@ struct FastCfg {
     static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
+int g_fwd_variant = 0;  // msda_set_tuning("fwd_variant", 0|1|2): experiment switch, results never depend on it
+
 struct FastArgs {
     int M, L, P, Lq, S;
     int cell_bytes;            // M * D * 4
@@ -45,8 +47,10 @@ struct FastArgs {
     int64_t value_batch_stride;  // elements
 };
 
-template <int LANES, int PAIRS, int CSB>
-__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
+// VAR (experiments, msda_set_tuning("fwd_variant")): 0 = one sample per step; 1 = two samples per
+// step (gather_fma2); 2 = as 0 with the register cap that admits 10 CTAs per SM.
+template <int LANES, int PAIRS, int CSB, int VAR = 0>
+__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS, VAR == 2 ? 1920 / FastCfg<LANES, PAIRS>::THREADS : (VAR == 1 ? 960 / FastCfg<LANES, PAIRS>::THREADS : 0))
 msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                      const float *__restrict__ attn, float *__restrict__ out, const FastArgs a)
@@ -55,7 +59,7 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *wts = reinterpret_cast<float4 *>(smem_raw);
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * a.cl);
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1));
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
@@ -92,15 +96,22 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
                 w = make_float4(hy * hx * at, hy * s.lx * at, s.ly * hx * at, s.ly * s.lx * at);
             }
             meta[i] = mt;
-            wts[i] = w;
+            wts[i + spl] = w;  // 16-byte records are strided n + 1 per query: no LDS.128 bank conflicts
         }
         __syncthreads();
         // ---- phase 2: gather ----
         if (live) {
             const SampleMeta *mm = meta + pl * n;
-            const float4 *ww = wts + pl * n;
+            const float4 *ww = wts + pl * (n + 1);
+            if (VAR == 1) {
+                int j = 0;
+#pragma unroll 2
+                for (; j + 1 < n; j += 2) gather_fma2<CSB>(acc, mm[j], ww[j], mm[j + 1], ww[j + 1], p0, a.cell_bytes);
+                if (j < n) gather_fma<CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
+            } else {
 #pragma unroll 4
-            for (int j = 0; j < n; ++j) gather_fma<CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
+                for (int j = 0; j < n; ++j) gather_fma<CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
+            }
         }
         if (lp0 + a.cl < LP) __syncthreads();  // staging buffers are reused by the next pass
     }
@@ -121,8 +132,9 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * a.cl);
-    float *part = reinterpret_cast<float *>(smem_raw + (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * a.cl);
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1));
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1) +
+                                            sizeof(SampleMeta) * Cfg::PAIRS * a.cl);
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
@@ -160,20 +172,20 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
                 f = make_float4(s.lx, s.ly, __ldg(attn + si), 0.f);
             }
             meta[i] = mt;
-            frac[i] = f;
+            frac[i + spl] = f;  // stride n + 1 per query (bank-conflict-free LDS.128)
         }
         __syncthreads();
         // ---- phase 2: gather + scatter; every thread runs it (full-mask shuffles) ----
         {
             const SampleMeta *mm = meta + pl * n;
-            const float4 *ff = frac + pl * n;
+            const float4 *ff = frac + pl * (n + 1);
             float *mypart = part + (size_t)(pl * n) * (Cfg::SUBS * 3) + sub * 3;
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
                 const float4 f = ff[j];
-                const float4 ga = make_float4(g.x * f.z, g.y * f.z, g.z * f.z, g.w * f.z);
+                const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
                 float pa = 0.f, px = 0.f, py = 0.f;
-                gather_scatter<CSB, SCATTER>(mm[j], f.x, f.y, ga, g, p0, gp0, a.cell_bytes, pa, px, py);
+                gather_scatter<CSB, SCATTER>(mm[j], bw, g, p0, gp0, a.cell_bytes, pa, px, py);
                 subgroup_sum3(pa, px, py);
                 if ((lane & 3) == 0) {
                     float *dst = mypart + j * (Cfg::SUBS * 3);
@@ -191,7 +203,7 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
                 float pa = 0.f, px = 0.f, py = 0.f;
 #pragma unroll
                 for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
-                const float at = frac[i].z;
+                const float at = frac[i + spl].z;
                 const int l = fast_div(lp, a.magic_P);
                 const size_t si = (((size_t)nb * a.Lq + q0 + spl) * a.M + m) * LP + lp;
                 grad_attn[si] = pa;
@@ -241,11 +253,16 @@ static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, co
     using Cfg = FastCfg<LANES, PAIRS>;
     const FastArgs a = make_fast_args<LANES, PAIRS>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
-    const size_t smem = (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * a.cl;
-    if (LANES == 12 && d.M == 8)  // Snipper: cell stride 1536 B becomes an immediate offset
-        msda_fwd_fast_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(
-            value, shapes, lsi, loc, attn, out, a);
-    else
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) + sizeof(SampleMeta) * Cfg::PAIRS * a.cl;
+    if (LANES == 12 && d.M == 8) {  // Snipper: cell stride 1536 B becomes an immediate offset
+        constexpr int C = LANES == 12 ? 1536 : 0;
+        if (g_fwd_variant == 1)
+            msda_fwd_fast_kernel<LANES, PAIRS, C, (LANES == 12 ? 1 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+        else if (g_fwd_variant == 2)
+            msda_fwd_fast_kernel<LANES, PAIRS, C, (LANES == 12 ? 2 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+        else
+            msda_fwd_fast_kernel<LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+    } else
         msda_fwd_fast_kernel<LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
     return cudaGetLastError();
 }
@@ -259,7 +276,8 @@ static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, co
     using Cfg = FastCfg<LANES, PAIRS>;
     const FastArgs a = make_fast_args<LANES, PAIRS>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
-    const size_t smem = (sizeof(float4) + sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * a.cl;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) +
+                        (sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * a.cl;
     if (LANES == 12 && d.M == 8)
         msda_bwd_fast_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0), SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
@@ -273,10 +291,12 @@ static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, co
     switch ((D) / 4) {                                                \
         case 4: return CALL(4, 16);                                   \
         case 8: return CALL(8, 16);                                   \
-        case 12:                                                      \
-            if (g_pairs_d48 == 8) return CALL(12, 8);                 \
-            if (g_pairs_d48 == 32) return CALL(12, 32);               \
+        case 12: {                                                    \
+            const int pairs_ = pick_pairs_d48(g_pairs_d48, d.Lq, d.M, d.N); \
+            if (pairs_ == 8) return CALL(12, 8);                      \
+            if (pairs_ == 32) return CALL(12, 32);                    \
             return CALL(12, 16);                                      \
+        }                                                             \
         case 16: return CALL(16, 16);                                 \
         case 20: return CALL(20, 16);                                 \
         case 24: return CALL(24, 16);                                 \

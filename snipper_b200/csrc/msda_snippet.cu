@@ -102,7 +102,7 @@ __device__ __forceinline__ void snippet_phase1(SampleMeta *meta, float4 *second,
             }
         }
         meta[i] = mt;
-        second[i] = sec;
+        second[i + spl] = sec;  // 16-byte records strided LP + 1 per query (bank-conflict-free LDS.128)
     }
     __syncthreads();
 }
@@ -120,8 +120,9 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
     float4 *wts = reinterpret_cast<float4 *>(smem_raw);
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * LP);
-    float *zs = reinterpret_cast<float *>(smem_raw + (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * LP);
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
+    float *zs = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1) +
+                                          sizeof(SampleMeta) * Cfg::PAIRS * LP);
     float *es = zs + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
@@ -146,7 +147,7 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
                      (size_t)(m * LANES + lane) * 16;
     const int64_t fstride = d.value_stride_t * 4;  // bytes between frames
     const SampleMeta *mm = meta + pl * LP;
-    const float4 *ww = wts + pl * LP;
+    const float4 *ww = wts + pl * (LP + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < LP; ++j) gather_fma_frames<CSB>(acc, mm[j], ww[j], pf, fstride, nf, a.cell_bytes);
     reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
@@ -167,8 +168,9 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
     float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * LP);
-    float *part = reinterpret_cast<float *>(smem_raw + (sizeof(float4) + sizeof(SampleMeta)) * Cfg::PAIRS * LP);
+    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1) +
+                                            sizeof(SampleMeta) * Cfg::PAIRS * LP);
     float *zs = part;  // phase-1 scratch aliases `part` ([rec][SUBS][3] >= 2 floats per record)
     float *es = part + Cfg::PAIRS * LP;
 
@@ -201,17 +203,17 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
         const int64_t fstride = d.value_stride_t * 4;
         const int64_t gfstride = (int64_t)d.S * a.cell_bytes;
         const SampleMeta *mm = meta + pl * LP;
-        const float4 *ff = frac + pl * LP;
+        const float4 *ff = frac + pl * (LP + 1);
         float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
         for (int j = 0; j < LP; ++j) {
             const SampleMeta mt = mm[j];
             const float4 f = ff[j];
-            const float4 ga = make_float4(g.x * f.z, g.y * f.z, g.z * f.z, g.w * f.z);
+            const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
             float pa = 0.f, px = 0.f, py = 0.f;
             const char *p0 = pf;
             char *gp0 = gpf;
             for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
-                gather_scatter<CSB, true>(mt, f.x, f.y, ga, g, p0, gp0, a.cell_bytes, pa, px, py);
+                gather_scatter<CSB, true>(mt, bw, g, p0, gp0, a.cell_bytes, pa, px, py);
             subgroup_sum3(pa, px, py);
             // zs/es alias `part`: all phase-1 reads finished at the barrier that ends phase 1
             if ((lane & 3) == 0) {
@@ -232,8 +234,8 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
 #pragma unroll
         for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
         pa_i[it] = pa;
-        const float at = frac[i].z;
         const int spl = fast_div(i, a.magic_LP);
+        const float at = frac[i + spl].z;
         if (q0 + spl < d.Lq) {
             // loc = ref + off/(W,H) and x = loc*W - 0.5  =>  dx/doff_x = 1: the W factor of the
             // per-call grad_loc (W*A*px) cancels against the 1/W of the normalisation.
@@ -250,7 +252,7 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
             float dot = 0.f;
             for (int j = 0; j < LP; ++j) dot += part[(size_t)(spl * LP + j) * (Cfg::SUBS * 3)];
             const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
-            grad_logits[si] = frac[i].z * (pa_i[it] - (float)nf * dot);
+            grad_logits[si] = frac[i + spl].z * (pa_i[it] - (float)nf * dot);
         }
     }
 }
@@ -285,7 +287,8 @@ static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, co
     using Cfg = SnipCfg<LANES, PAIRS>;
     const SnipArgs a = make_snip_args(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = (sizeof(float4) + sizeof(SampleMeta) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) +
+                        (sizeof(SampleMeta) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
     if (LANES == 12 && d.M == 8)
         msda_snippet_fwd_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, offsets, logits, ref, out, a);
@@ -304,7 +307,8 @@ static cudaError_t launch_snip_bwd_impl(const float *value, const int64_t *shape
     using Cfg = SnipCfg<LANES, PAIRS>;
     const SnipArgs a = make_snip_args(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = (sizeof(float4) + sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) +
+                        (sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(msda_snippet_bwd_kernel<LANES, PAIRS, CSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     msda_snippet_bwd_kernel<LANES, PAIRS, CSB><<<grid, Cfg::THREADS, smem, stream>>>(
@@ -329,10 +333,12 @@ static cudaError_t launch_snip_bwd(const float *value, const int64_t *shapes, co
     switch ((D) / 4) {                                                \
         case 4: return CALL(4, 16);                                   \
         case 8: return CALL(8, 16);                                   \
-        case 12:                                                      \
-            if (g_snip_pairs_d48 == 8) return CALL(12, 8);            \
-            if (g_snip_pairs_d48 == 32) return CALL(12, 32);          \
+        case 12: {                                                    \
+            const int pairs_ = pick_pairs_d48(g_snip_pairs_d48, d.Lq, d.M, d.N * d.T1); \
+            if (pairs_ == 8) return CALL(12, 8);                      \
+            if (pairs_ == 32) return CALL(12, 32);                    \
             return CALL(12, 16);                                      \
+        }                                                             \
         case 16: return CALL(16, 16);                                 \
         case 20: return CALL(20, 8);                                  \
         case 24: return CALL(24, 8);                                  \

@@ -70,10 +70,14 @@ def make(N, Lq, M=8, D=48, P=4, levels=LEVELS, regime="local", device="cuda", se
 WARMUP = 5
 
 
-def time_fn(fn, iters, flush, inner=10):
+INNER = 10
+
+
+def time_fn(fn, iters, flush, inner=None):
     """Per-launch device time in us.  Without --flush: `inner` back-to-back launches between two
     events (host launch overhead hidden behind the queue).  With --flush: a 256 MiB memset evicts
     L2 before every single launch; the memset also keeps the queue busy, hiding host overhead."""
+    inner = inner or INNER
     buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if flush else None
     for _ in range(WARMUP):
         fn()
@@ -128,7 +132,17 @@ def direct_calls(value, shapes, lsi, loc, attn, go):
                             0, 64, 0, capi.MSDA_FLAG_ACCUMULATE_VALUE, 0, 0, st)
         assert r == 0, r
 
-    return fwd, bwd, bwd_nomemset, keep
+    ws_bytes = L.msda_backward_workspace_bytes(N, S, M, D, Lv, Lq, P, 0, capi.MSDA_FLAG_DETERMINISTIC)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=value.device)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+
+    def bwd_det():
+        r = L.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                            go.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), N, S, M, D, Lv, Lq, P,
+                            0, 64, 0, capi.MSDA_FLAG_DETERMINISTIC, ws_ptr, ws_bytes, st)
+        assert r == 0, r
+
+    return fwd, bwd, bwd_nomemset, bwd_det, keep + (ws,)
 
 
 def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encoder=True, seed=0, regime="local"):
@@ -196,15 +210,22 @@ def main():
     ap.add_argument("--regime", default="local")
     ap.add_argument("--pairs", type=int, default=0, help="tile length knob for D=48 (8/16/32)")
     ap.add_argument("--snip-pairs", type=int, default=0)
+    ap.add_argument("--fwd-variant", type=int, default=0, help="msda_set_tuning('fwd_variant') experiment switch")
+    ap.add_argument("--head-major", action="store_true",
+                    help="also time the per-call kernels on a head-major copy (value (N*M,S,1,D)): what a packed value layout would give")
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--inner", type=int, default=10, help="back-to-back launches per timed interval")
     ap.add_argument("--cases", default="snip_enc_N1,snip_dec_N1,enc_N1,enc_N2,enc_N8,dec_N1,dec_N2")
     args = ap.parse_args()
-    global WARMUP
+    global WARMUP, INNER
     WARMUP = args.warmup
+    INNER = args.inner
     import snipper_b200  # noqa: F401
     from snipper_b200 import capi
     if args.pairs:
         assert capi.lib().msda_set_tuning(b"pairs_d48", args.pairs) == 0
+    if args.fwd_variant:
+        assert capi.lib().msda_set_tuning(b"fwd_variant", args.fwd_variant) == 0
     ref = None
     if args.ref:
         from oracle.build_ref import load_ref
@@ -230,17 +251,27 @@ def main():
             continue
         value, shapes, lsi, loc, attn, go = make(N, Lq, regime=args.regime)
         fb, bb = algorithmic_bytes(N, S, 8, 48, 3, 4, Lq)
-        fwd, bwd, bwd_nm, keep = direct_calls(value, shapes, lsi, loc, attn, go)
-        rows = [("ours", "fwd", fwd, fb), ("ours", "bwd", bwd, bb), ("ours", "bwd_nomemset", bwd_nm, bb)]
+        fwd, bwd, bwd_nm, bwd_det, keep = direct_calls(value, shapes, lsi, loc, attn, go)
+        rows = [("ours", "fwd", fwd, fb), ("ours", "bwd", bwd, bb), ("ours", "bwd_nomemset", bwd_nm, bb),
+                ("ours", "bwd_deterministic", bwd_det, bb)]
         if ref is not None:
             rows += [("vendored", "fwd", lambda: ref.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 64), fb),
                      ("vendored", "bwd", lambda: ref.ms_deform_attn_backward(value, shapes, lsi, loc, attn, go, 64), bb)]
+        if args.head_major:
+            N_, S_, M_, D_ = value.shape
+            hv = value.permute(0, 2, 1, 3).reshape(N_ * M_, S_, 1, D_).contiguous()
+            hl = loc.permute(0, 2, 1, 3, 4, 5).reshape(N_ * M_, Lq, 1, 3, 4, 2).contiguous()
+            ha = attn.permute(0, 2, 1, 3, 4).reshape(N_ * M_, Lq, 1, 3, 4).contiguous()
+            hg = go.view(N_, Lq, M_, D_).permute(0, 2, 1, 3).reshape(N_ * M_, Lq, D_).contiguous()
+            hfwd, hbwd, hbwd_nm, _, hkeep = direct_calls(hv, shapes, lsi, hl, ha, hg)
+            rows += [("ours_head_major", "fwd", hfwd, fb), ("ours_head_major", "bwd", hbwd, bb)]
         for impl, which, fn, nbytes in rows:
             med, best = time_fn(fn, args.iters, args.flush)
             print(json.dumps({"case": name, "impl": impl, "pass": which, "us_median": round(med, 2),
                               "us_best": round(best, 2), "alg_MB": round(nbytes / 1e6, 2),
                               "GBps": round(nbytes / med / 1e3, 1), "frac_of_measured_hbm": round(nbytes / med / 1e3 / PEAK, 4),
-                              "l2_flush": args.flush, "regime": args.regime, "pairs": args.pairs or 16}))
+                              "l2_flush": args.flush, "regime": args.regime, "pairs": args.pairs or 16,
+                              "fwd_variant": args.fwd_variant}))
 
 
 if __name__ == "__main__":
