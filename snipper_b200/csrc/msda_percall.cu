@@ -37,7 +37,7 @@ struct FastCfg {
     static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
-int g_fwd_variant = 0;  // msda_set_tuning("fwd_variant", 0|1|2): experiment switch, results never depend on it
+int g_fwd_variant = 1;  // msda_set_tuning("fwd_variant", 0|1|2): 1 (two samples per step) measured best, profiles/r01_run9_*
 
 struct FastArgs {
     int M, L, P, Lq, S;

@@ -210,7 +210,7 @@ def main():
     ap.add_argument("--regime", default="local")
     ap.add_argument("--pairs", type=int, default=0, help="tile length knob for D=48 (8/16/32)")
     ap.add_argument("--snip-pairs", type=int, default=0)
-    ap.add_argument("--fwd-variant", type=int, default=0, help="msda_set_tuning('fwd_variant') experiment switch")
+    ap.add_argument("--fwd-variant", type=int, default=-1, help="msda_set_tuning('fwd_variant') experiment switch")
     ap.add_argument("--head-major", action="store_true",
                     help="also time the per-call kernels on a head-major copy (value (N*M,S,1,D)): what a packed value layout would give")
     ap.add_argument("--warmup", type=int, default=5)
@@ -224,7 +224,7 @@ def main():
     from snipper_b200 import capi
     if args.pairs:
         assert capi.lib().msda_set_tuning(b"pairs_d48", args.pairs) == 0
-    if args.fwd_variant:
+    if args.fwd_variant >= 0:
         assert capi.lib().msda_set_tuning(b"fwd_variant", args.fwd_variant) == 0
     ref = None
     if args.ref:
