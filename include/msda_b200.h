@@ -61,7 +61,10 @@ typedef enum {
 typedef enum {
     MSDA_DTYPE_F32 = 0,
     MSDA_DTYPE_F64 = 1,
-    MSDA_DTYPE_BF16 = 2 /* value/output/grad_output in bf16, fp32 accumulate; loc/attn stay fp32 */
+    MSDA_DTYPE_BF16 = 2 /* value / output / grad_output are bf16; sampling_loc, attn_weight (offsets,
+                           logits, reference_points) and EVERY gradient buffer -- grad_value too --
+                           are fp32; all arithmetic and accumulation is fp32.  D % 16 == 0 only
+                           (MSDA_ERR_UNSUPPORTED_DTYPE otherwise); no deterministic mode. */
 } msda_dtype_t;
 
 /* msda_backward / msda_snippet_backward flags */
@@ -120,7 +123,8 @@ MSDA_API size_t msda_backward_workspace_bytes(int batch, int spatial_size, int n
  * {t1-1,t1,t1+1} clipped to [0,n_frame) for t1 < n_frame, all T2 frames otherwise
  * (ms_deform_attn.py:137-140,189,201).  Requires the frame slots to share one Linear
  * (ms_deform_attn.py:68-71), which makes logits/offsets identical across t2.
- * float32 only; L*P <= 32; D % 16 == 0; D <= 128.
+ * MSDA_DTYPE_F32 or MSDA_DTYPE_BF16 (bf16 value / output, fp32 offsets / logits / reference
+ * points); L*P <= 32; D % 16 == 0; D <= 128.
  */
 MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
                          const int64_t *level_start_index, const void *offsets, const void *logits,

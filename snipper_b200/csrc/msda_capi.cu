@@ -96,8 +96,8 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     msda::OpDims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, value_batch_stride};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (spatial_size == 0) {  // nothing to sample: every corner is invalid
-        const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : 4;
-        if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64) return MSDA_ERR_UNSUPPORTED_DTYPE;
+        const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : (dtype == MSDA_DTYPE_BF16 ? 2 : 4);
+        if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
         return cuda_status(cudaMemsetAsync(output, 0, esz * batch * num_query * num_heads * channels, s));
     }
     switch (dtype) {
@@ -113,6 +113,12 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
             return cuda_status(msda::launch_forward_generic<double>(
                 (const double *)value, spatial_shapes, level_start_index, (const double *)sampling_loc,
                 (const double *)attn_weight, (double *)output, d, s));
+        case MSDA_DTYPE_BF16:
+            // vectorised path only: D % 16 == 0 (16-byte lanes of 8 channels, an even number of lanes)
+            if (!(msda::fast_path_ok(d, 2) && aligned16(value) && aligned16(output))) return MSDA_ERR_UNSUPPORTED_DTYPE;
+            return cuda_status(msda::launch_forward_fast_bf16(
+                value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+                (const float *)attn_weight, output, d, s));
         default:
             return MSDA_ERR_UNSUPPORTED_DTYPE;
     }
@@ -140,12 +146,12 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     if (st != MSDA_OK) return st;
     st = check_im2col_step(batch, im2col_step);
     if (st != MSDA_OK) return st;
-    if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
     if (value_batch_stride == 0) value_batch_stride = (int64_t)spatial_size * num_heads * channels;
     if (value_batch_stride < 0) return MSDA_ERR_INVALID_ARGUMENT;
     msda::OpDims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, value_batch_stride};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : 4;
+    const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : 4;  // bf16 mode: every gradient buffer is fp32
     const size_t value_elems = (size_t)batch * spatial_size * num_heads * channels;
     if (!(flags & MSDA_FLAG_ACCUMULATE_VALUE) && value_elems > 0 && grad_value != nullptr) {
         st = cuda_status(cudaMemsetAsync(grad_value, 0, esz * value_elems, s));
@@ -164,6 +170,15 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
             (const double *)value, spatial_shapes, level_start_index, (const double *)sampling_loc,
             (const double *)attn_weight, (const double *)grad_output, (double *)grad_value,
             (double *)grad_sampling_loc, (double *)grad_attn_weight, d, s));
+    }
+    if (dtype == MSDA_DTYPE_BF16) {
+        if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_UNSUPPORTED_DTYPE;
+        if (!(msda::fast_path_ok(d, 2) && aligned16(value) && aligned16(grad_output) && aligned16(grad_value)))
+            return MSDA_ERR_UNSUPPORTED_DTYPE;
+        return cuda_status(msda::launch_backward_fast_bf16(
+            value, spatial_shapes, level_start_index, (const float *)sampling_loc,
+            (const float *)attn_weight, grad_output, (float *)grad_value,
+            (float *)grad_sampling_loc, (float *)grad_attn_weight, d, s));
     }
     if (flags & MSDA_FLAG_DETERMINISTIC) {
         const size_t need = msda::deterministic_workspace_bytes(d);
@@ -191,7 +206,7 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
                         int num_query, int num_point, int64_t value_stride_n, int64_t value_stride_t,
                         int64_t ref_stride_n, int64_t ref_stride_t, int dtype)
 {
-    if (dtype != MSDA_DTYPE_F32) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
     if (batch < 0 || num_query < 0 || n_src_frames <= 0 || n_query_frames <= 0 || n_frame <= 0 ||
         n_frame > n_src_frames || spatial_size <= 0 || num_heads <= 0 || channels <= 0 ||
         num_levels <= 0 || num_point <= 0)
@@ -203,7 +218,7 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
     d = msda::SnippetDims{batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t};
-    if (!msda::snippet_ok(d)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (!msda::snippet_ok(d, dtype == MSDA_DTYPE_BF16 ? 2 : 4)) return MSDA_ERR_INVALID_ARGUMENT;
     return MSDA_OK;
 }
 
@@ -226,6 +241,10 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
         return MSDA_ERR_INVALID_ARGUMENT;
     if (!aligned16(value) || !aligned16(output) || !aligned16(offsets) || !aligned16(logits))
         return MSDA_ERR_INVALID_ARGUMENT;
+    if (dtype == MSDA_DTYPE_BF16)
+        return cuda_status(msda::launch_snippet_forward_bf16(
+            value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
+            (const float *)reference_points, output, d, static_cast<cudaStream_t>(stream)));
     return cuda_status(msda::launch_snippet_forward_f32(
         (const float *)value, spatial_shapes, level_start_index, (const float *)offsets,
         (const float *)logits, (const float *)reference_points, (float *)output, d,
@@ -262,6 +281,11 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
         return MSDA_ERR_INVALID_ARGUMENT;
     if (!aligned16(value) || !aligned16(grad_output) || !aligned16(grad_value))
         return MSDA_ERR_INVALID_ARGUMENT;
+    if (dtype == MSDA_DTYPE_BF16)
+        return cuda_status(msda::launch_snippet_backward_bf16(
+            value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
+            (const float *)reference_points, grad_output, (float *)grad_value, (float *)grad_offsets,
+            (float *)grad_logits, d, s));
     return cuda_status(msda::launch_snippet_backward_f32(
         (const float *)value, spatial_shapes, level_start_index, (const float *)offsets,
         (const float *)logits, (const float *)reference_points, (const float *)grad_output,

@@ -21,6 +21,8 @@
 // HBM traffic is only the compulsory ~42 MB per call.
 #pragma once
 
+#include <cuda_bf16.h>
+
 #include "msda_common.cuh"
 
 namespace msda {
@@ -56,91 +58,267 @@ __device__ __forceinline__ SampleMeta empty_meta()
 template <int CSB>
 __device__ __forceinline__ int cell_stride_bytes(int runtime_csb) { return CSB > 0 ? CSB : runtime_csb; }
 
+// ------------------------------------------------------------------------------------------
+// 16-byte channel chunk of the value / output / grad_output element type VT, widened to fp32:
+//   float          4 channels  (LDG.E.128 -> 4 registers used as they are)
+//   __nv_bfloat16  8 channels  (LDG.E.128 -> 4 registers, each split with one shift / one mask)
+// All arithmetic is fp32 whatever VT is.
+// ------------------------------------------------------------------------------------------
+template <typename VT> struct Chunk;
+
+template <> struct Chunk<float> {
+    using elem = float;
+    static constexpr int N = 4;
+    static constexpr int BYTES = 16;
+    float x[4];
+    static __device__ __forceinline__ Chunk load(const char *p)
+    {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        Chunk c;
+        c.x[0] = v.x; c.x[1] = v.y; c.x[2] = v.z; c.x[3] = v.w;
+        return c;
+    }
+    __device__ __forceinline__ void store(char *p) const
+    {
+        *reinterpret_cast<float4 *>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    }
+};
+
+template <> struct Chunk<__nv_bfloat16> {
+    using elem = __nv_bfloat16;
+    static constexpr int N = 8;
+    static constexpr int BYTES = 16;
+    float x[8];
+    static __device__ __forceinline__ Chunk load(const char *p)
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        Chunk c;
+        c.x[0] = __uint_as_float(v.x << 16); c.x[1] = __uint_as_float(v.x & 0xffff0000u);
+        c.x[2] = __uint_as_float(v.y << 16); c.x[3] = __uint_as_float(v.y & 0xffff0000u);
+        c.x[4] = __uint_as_float(v.z << 16); c.x[5] = __uint_as_float(v.z & 0xffff0000u);
+        c.x[6] = __uint_as_float(v.w << 16); c.x[7] = __uint_as_float(v.w & 0xffff0000u);
+        return c;
+    }
+    __device__ __forceinline__ void store(char *p) const
+    {
+        uint4 v;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(x[0], x[1]); v.x = *reinterpret_cast<unsigned *>(&t);
+        t = __floats2bfloat162_rn(x[2], x[3]); v.y = *reinterpret_cast<unsigned *>(&t);
+        t = __floats2bfloat162_rn(x[4], x[5]); v.z = *reinterpret_cast<unsigned *>(&t);
+        t = __floats2bfloat162_rn(x[6], x[7]); v.w = *reinterpret_cast<unsigned *>(&t);
+        *reinterpret_cast<uint4 *>(p) = v;
+    }
+};
+
+// 8-byte lane of 4 bf16 channels: the BACKWARD lane type for bf16.  With 4 channels per lane the
+// fp32 grad_value bytes a lane owns are one contiguous 16-byte vector reduction, exactly as in the
+// fp32 kernels; the 16-byte lane of 8 channels would need two half-filled reductions per corner
+// (measured 25 % slower, profiles/r01_run12_*).
+struct bf16q {};
+
+template <> struct Chunk<bf16q> {
+    using elem = __nv_bfloat16;
+    static constexpr int N = 4;
+    static constexpr int BYTES = 8;
+    float x[4];
+    static __device__ __forceinline__ Chunk load(const char *p)
+    {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        Chunk c;
+        c.x[0] = __uint_as_float(v.x << 16); c.x[1] = __uint_as_float(v.x & 0xffff0000u);
+        c.x[2] = __uint_as_float(v.y << 16); c.x[3] = __uint_as_float(v.y & 0xffff0000u);
+        return c;
+    }
+    __device__ __forceinline__ void store(char *p) const
+    {
+        uint2 v;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(x[0], x[1]); v.x = *reinterpret_cast<unsigned *>(&t);
+        t = __floats2bfloat162_rn(x[2], x[3]); v.y = *reinterpret_cast<unsigned *>(&t);
+        *reinterpret_cast<uint2 *>(p) = v;
+    }
+};
+
+template <typename C>
+__device__ __forceinline__ C zero_chunk()
+{
+    C c;
+#pragma unroll
+    for (int i = 0; i < C::N; ++i) c.x[i] = 0.f;
+    return c;
+}
+
+template <typename C>
+__device__ __forceinline__ void fma_chunk(C &acc, float w, const C &v)
+{
+#pragma unroll
+    for (int i = 0; i < C::N; ++i) acc.x[i] = fmaf(w, v.x[i], acc.x[i]);
+}
+
+template <typename C>
+__device__ __forceinline__ float dot_chunk(const C &a, const C &b)
+{
+    float d = a.x[C::N - 1] * b.x[C::N - 1];
+#pragma unroll
+    for (int i = C::N - 2; i >= 0; --i) d = fmaf(a.x[i], b.x[i], d);
+    return d;
+}
+
+// grad_value is accumulated in fp32 whatever VT is.  A lane that gathers C::N channels owns
+// C::N * 4 bytes of the fp32 slice.  fp32: one 128-bit vector reduction at byte 16 * lane.
+// bf16: two, and they must not be the lane's own 32 contiguous bytes -- each instruction would
+// then touch every 32-byte sector of the slice half-filled and double the L2 request count.
+// Instead lanes pair up (2j, 2j+1) over 64 bytes: instruction A writes bytes [0,32) of the pair
+// (16 each), instruction B bytes [32,64).  `RedView` holds G's channels in that arrangement
+// (swapped once per pair of lanes with four shuffles), `red_lane_offset` the matching address.
+template <typename VT> struct RedView;
+
+template <> struct RedView<float> {
+    float x[4];
+    static __device__ __forceinline__ RedView make(const Chunk<float> &g)
+    {
+        RedView r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.x[i] = g.x[i];
+        return r;
+    }
+    static __device__ __forceinline__ int lane_offset(int lane) { return lane * 16; }
+    __device__ __forceinline__ void red(char *gp, float a) const
+    {
+        red_add_v4(reinterpret_cast<float *>(gp), a * x[0], a * x[1], a * x[2], a * x[3]);
+    }
+};
+
+template <> struct RedView<bf16q> {
+    float x[4];
+    static __device__ __forceinline__ RedView make(const Chunk<bf16q> &g)
+    {
+        RedView r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.x[i] = g.x[i];
+        return r;
+    }
+    static __device__ __forceinline__ int lane_offset(int lane) { return lane * 16; }
+    __device__ __forceinline__ void red(char *gp, float a) const
+    {
+        red_add_v4(reinterpret_cast<float *>(gp), a * x[0], a * x[1], a * x[2], a * x[3]);
+    }
+};
+
+template <> struct RedView<__nv_bfloat16> {
+    float x[8];  // [0,4): what instruction A writes, [4,8): instruction B
+    // every lane of the warp must call this (full-mask shuffles); LANES is even, so (2j, 2j+1) never
+    // straddles a query
+    static __device__ __forceinline__ RedView make(const Chunk<__nv_bfloat16> &g)
+    {
+        const bool odd = threadIdx.x & 1;
+        RedView r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = odd ? g.x[i] : g.x[4 + i];          // the half the partner writes
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            r.x[i] = odd ? recv : g.x[i];                          // A: channels 16j + 4*(lane&1) + i
+            r.x[4 + i] = odd ? g.x[4 + i] : recv;                  // B: channels 16j + 8 + 4*(lane&1) + i
+        }
+        return r;
+    }
+    static __device__ __forceinline__ int lane_offset(int lane) { return (lane >> 1) * 64 + (lane & 1) * 16; }
+    __device__ __forceinline__ void red(char *gp, float a) const
+    {
+        red_add_v4(reinterpret_cast<float *>(gp), a * x[0], a * x[1], a * x[2], a * x[3]);
+        red_add_v4(reinterpret_cast<float *>(gp + 32), a * x[4], a * x[5], a * x[6], a * x[7]);
+    }
+};
+
 // Forward gather of one sample for this lane: acc += sum_k w_k * V[corner_k]
-template <int CSB>
-__device__ __forceinline__ void gather_fma(float4 &acc, const SampleMeta mt, const float4 w,
+template <typename VT, int CSB>
+__device__ __forceinline__ void gather_fma(Chunk<VT> &acc, const SampleMeta mt, const float4 w,
                                            const char *__restrict__ p0, int runtime_csb)
 {
+    using C = Chunk<VT>;
     const int csb = cell_stride_bytes<CSB>(runtime_csb);
     const char *a0 = p0 + (ptrdiff_t)mt.off;
     const char *a2 = a0 + (mt.wm & 0x0fffffffu);
     if (mt.wm >= kAllCorners) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(a0));
-        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(a0 + csb));
-        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(a2));
-        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(a2 + csb));
-        fma4(acc, w.x, v0);
-        fma4(acc, w.y, v1);
-        fma4(acc, w.z, v2);
-        fma4(acc, w.w, v3);
+        const C v0 = C::load(a0);
+        const C v1 = C::load(a0 + csb);
+        const C v2 = C::load(a2);
+        const C v3 = C::load(a2 + csb);
+        fma_chunk(acc, w.x, v0);
+        fma_chunk(acc, w.y, v1);
+        fma_chunk(acc, w.z, v2);
+        fma_chunk(acc, w.w, v3);
     } else {
         const unsigned mask = mt.wm >> 28;
-        if (mask & 1u) fma4(acc, w.x, __ldg(reinterpret_cast<const float4 *>(a0)));
-        if (mask & 2u) fma4(acc, w.y, __ldg(reinterpret_cast<const float4 *>(a0 + csb)));
-        if (mask & 4u) fma4(acc, w.z, __ldg(reinterpret_cast<const float4 *>(a2)));
-        if (mask & 8u) fma4(acc, w.w, __ldg(reinterpret_cast<const float4 *>(a2 + csb)));
+        if (mask & 1u) fma_chunk(acc, w.x, C::load(a0));
+        if (mask & 2u) fma_chunk(acc, w.y, C::load(a0 + csb));
+        if (mask & 4u) fma_chunk(acc, w.z, C::load(a2));
+        if (mask & 8u) fma_chunk(acc, w.w, C::load(a2 + csb));
     }
 }
 
 // Two samples per step: when both have all four corners, the eight gathers are issued before any
-// of the 32 FFMAs so twice as many loads are in flight per warp.
-template <int CSB>
-__device__ __forceinline__ void gather_fma2(float4 &acc, const SampleMeta m0, const float4 w0, const SampleMeta m1,
+// of the FFMAs so twice as many loads are in flight per warp.
+template <typename VT, int CSB>
+__device__ __forceinline__ void gather_fma2(Chunk<VT> &acc, const SampleMeta m0, const float4 w0, const SampleMeta m1,
                                             const float4 w1, const char *__restrict__ p0, int runtime_csb)
 {
+    using C = Chunk<VT>;
     const int csb = cell_stride_bytes<CSB>(runtime_csb);
     if (m0.wm >= kAllCorners && m1.wm >= kAllCorners) {
         const char *a0 = p0 + (ptrdiff_t)m0.off;
         const char *a2 = a0 + (m0.wm & 0x0fffffffu);
         const char *b0 = p0 + (ptrdiff_t)m1.off;
         const char *b2 = b0 + (m1.wm & 0x0fffffffu);
-        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(a0));
-        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(a0 + csb));
-        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(a2));
-        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(a2 + csb));
-        const float4 u0 = __ldg(reinterpret_cast<const float4 *>(b0));
-        const float4 u1 = __ldg(reinterpret_cast<const float4 *>(b0 + csb));
-        const float4 u2 = __ldg(reinterpret_cast<const float4 *>(b2));
-        const float4 u3 = __ldg(reinterpret_cast<const float4 *>(b2 + csb));
-        fma4(acc, w0.x, v0); fma4(acc, w0.y, v1); fma4(acc, w0.z, v2); fma4(acc, w0.w, v3);
-        fma4(acc, w1.x, u0); fma4(acc, w1.y, u1); fma4(acc, w1.z, u2); fma4(acc, w1.w, u3);
+        const C v0 = C::load(a0);
+        const C v1 = C::load(a0 + csb);
+        const C v2 = C::load(a2);
+        const C v3 = C::load(a2 + csb);
+        const C u0 = C::load(b0);
+        const C u1 = C::load(b0 + csb);
+        const C u2 = C::load(b2);
+        const C u3 = C::load(b2 + csb);
+        fma_chunk(acc, w0.x, v0); fma_chunk(acc, w0.y, v1); fma_chunk(acc, w0.z, v2); fma_chunk(acc, w0.w, v3);
+        fma_chunk(acc, w1.x, u0); fma_chunk(acc, w1.y, u1); fma_chunk(acc, w1.z, u2); fma_chunk(acc, w1.w, u3);
     } else {
-        gather_fma<CSB>(acc, m0, w0, p0, runtime_csb);
-        gather_fma<CSB>(acc, m1, w1, p0, runtime_csb);
+        gather_fma<VT, CSB>(acc, m0, w0, p0, runtime_csb);
+        gather_fma<VT, CSB>(acc, m1, w1, p0, runtime_csb);
     }
 }
 
 // Same, over `nf` consecutive value frames (fused snippet kernel): the sample set-up is shared by all
 // neighbour frames, so the fast/slow decision is taken once and the frame loop is branch-free,
 // which lets the loads of two frames overlap.
-template <int CSB>
-__device__ __forceinline__ void gather_fma_frames(float4 &acc, const SampleMeta mt, const float4 w,
+template <typename VT, int CSB>
+__device__ __forceinline__ void gather_fma_frames(Chunk<VT> &acc, const SampleMeta mt, const float4 w,
                                                   const char *__restrict__ pf, int64_t frame_bytes, int nf,
                                                   int runtime_csb)
 {
+    using C = Chunk<VT>;
     const int csb = cell_stride_bytes<CSB>(runtime_csb);
     const char *a0 = pf + (ptrdiff_t)mt.off;
     const ptrdiff_t row = (ptrdiff_t)(mt.wm & 0x0fffffffu);
     if (mt.wm >= kAllCorners) {
 #pragma unroll 2
         for (int f = 0; f < nf; ++f, a0 += frame_bytes) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(a0));
-            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(a0 + csb));
-            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(a0 + row));
-            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(a0 + row + csb));
-            fma4(acc, w.x, v0);
-            fma4(acc, w.y, v1);
-            fma4(acc, w.z, v2);
-            fma4(acc, w.w, v3);
+            const C v0 = C::load(a0);
+            const C v1 = C::load(a0 + csb);
+            const C v2 = C::load(a0 + row);
+            const C v3 = C::load(a0 + row + csb);
+            fma_chunk(acc, w.x, v0);
+            fma_chunk(acc, w.y, v1);
+            fma_chunk(acc, w.z, v2);
+            fma_chunk(acc, w.w, v3);
         }
     } else {
         const unsigned mask = mt.wm >> 28;
         if (mask == 0u) return;
         for (int f = 0; f < nf; ++f, a0 += frame_bytes) {
-            if (mask & 1u) fma4(acc, w.x, __ldg(reinterpret_cast<const float4 *>(a0)));
-            if (mask & 2u) fma4(acc, w.y, __ldg(reinterpret_cast<const float4 *>(a0 + csb)));
-            if (mask & 4u) fma4(acc, w.z, __ldg(reinterpret_cast<const float4 *>(a0 + row)));
-            if (mask & 8u) fma4(acc, w.w, __ldg(reinterpret_cast<const float4 *>(a0 + row + csb)));
+            if (mask & 1u) fma_chunk(acc, w.x, C::load(a0));
+            if (mask & 2u) fma_chunk(acc, w.y, C::load(a0 + csb));
+            if (mask & 4u) fma_chunk(acc, w.z, C::load(a0 + row));
+            if (mask & 8u) fma_chunk(acc, w.w, C::load(a0 + row + csb));
         }
     }
 }
@@ -164,45 +342,49 @@ __device__ __forceinline__ BwdWeights make_bwd_weights(float lx, float ly, float
 
 // Backward work of one sample for this lane on one value frame: scatter w_k*A*G into grad_value
 // (vector reductions) and accumulate the three per-sample partial dot products.
-// "Dot first": d_k = <G, V_k> over this lane's 4 channels, then
+// "Dot first": d_k = <G, V_k> over this lane's channels, then
 //     <G, val>      = sum_k w_k d_k
 //     <G, dval/dx>  = hy (d1 - d0) + ly (d3 - d2)
 //     <G, dval/dy>  = hx (d2 - d0) + lx (d3 - d1)
-// -- 28 FP instructions instead of the 60 of forming val / dval per channel and dotting after.
-template <int CSB, bool SCATTER>
-__device__ __forceinline__ void gather_scatter(const SampleMeta mt, const BwdWeights &b, const float4 g,
-                                               const char *__restrict__ p0, char *gp0,
+// -- 28 FP instructions (fp32) instead of the 60 of forming val / dval per channel and dotting after.
+// gp0 addresses the fp32 grad_value buffer (head slice + RedView::lane_offset): its cell byte
+// offsets are GS = 4 / sizeof(VT) times the value byte offsets held in the sample record.
+template <typename VT, int CSB, bool SCATTER>
+__device__ __forceinline__ void gather_scatter(const SampleMeta mt, const BwdWeights &b, const Chunk<VT> &g,
+                                               const RedView<VT> &gr, const char *__restrict__ p0, char *gp0,
                                                int runtime_csb, float &pa, float &px, float &py)
 {
+    using C = Chunk<VT>;
+    constexpr int GS = 4 / (int)sizeof(typename C::elem);
     const int csb = cell_stride_bytes<CSB>(runtime_csb);
     const ptrdiff_t o0 = (ptrdiff_t)mt.off;
     const ptrdiff_t o2 = o0 + (mt.wm & 0x0fffffffu);
     float d0, d1, d2, d3;
     if (mt.wm >= kAllCorners) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p0 + o0));
-        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p0 + o0 + csb));
-        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p0 + o2));
-        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p0 + o2 + csb));
+        const C v0 = C::load(p0 + o0);
+        const C v1 = C::load(p0 + o0 + csb);
+        const C v2 = C::load(p0 + o2);
+        const C v3 = C::load(p0 + o2 + csb);
         if (SCATTER) {
-            red_add_v4(reinterpret_cast<float *>(gp0 + o0), b.a0 * g.x, b.a0 * g.y, b.a0 * g.z, b.a0 * g.w);
-            red_add_v4(reinterpret_cast<float *>(gp0 + o0 + csb), b.a1 * g.x, b.a1 * g.y, b.a1 * g.z, b.a1 * g.w);
-            red_add_v4(reinterpret_cast<float *>(gp0 + o2), b.a2 * g.x, b.a2 * g.y, b.a2 * g.z, b.a2 * g.w);
-            red_add_v4(reinterpret_cast<float *>(gp0 + o2 + csb), b.a3 * g.x, b.a3 * g.y, b.a3 * g.z, b.a3 * g.w);
+            gr.red(gp0 + GS * o0, b.a0);
+            gr.red(gp0 + GS * (o0 + csb), b.a1);
+            gr.red(gp0 + GS * o2, b.a2);
+            gr.red(gp0 + GS * (o2 + csb), b.a3);
         }
-        d0 = dot4(g, v0); d1 = dot4(g, v1); d2 = dot4(g, v2); d3 = dot4(g, v3);
+        d0 = dot_chunk(g, v0); d1 = dot_chunk(g, v1); d2 = dot_chunk(g, v2); d3 = dot_chunk(g, v3);
     } else {
         const unsigned mask = mt.wm >> 28;
         if (mask == 0u) return;  // inactive sample contributes nothing anywhere
         d0 = 0.f; d1 = 0.f; d2 = 0.f; d3 = 0.f;
-        if (mask & 1u) d0 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o0)));
-        if (mask & 2u) d1 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o0 + csb)));
-        if (mask & 4u) d2 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o2)));
-        if (mask & 8u) d3 = dot4(g, __ldg(reinterpret_cast<const float4 *>(p0 + o2 + csb)));
+        if (mask & 1u) d0 = dot_chunk(g, C::load(p0 + o0));
+        if (mask & 2u) d1 = dot_chunk(g, C::load(p0 + o0 + csb));
+        if (mask & 4u) d2 = dot_chunk(g, C::load(p0 + o2));
+        if (mask & 8u) d3 = dot_chunk(g, C::load(p0 + o2 + csb));
         if (SCATTER) {
-            if (mask & 1u) red_add_v4(reinterpret_cast<float *>(gp0 + o0), b.a0 * g.x, b.a0 * g.y, b.a0 * g.z, b.a0 * g.w);
-            if (mask & 2u) red_add_v4(reinterpret_cast<float *>(gp0 + o0 + csb), b.a1 * g.x, b.a1 * g.y, b.a1 * g.z, b.a1 * g.w);
-            if (mask & 4u) red_add_v4(reinterpret_cast<float *>(gp0 + o2), b.a2 * g.x, b.a2 * g.y, b.a2 * g.z, b.a2 * g.w);
-            if (mask & 8u) red_add_v4(reinterpret_cast<float *>(gp0 + o2 + csb), b.a3 * g.x, b.a3 * g.y, b.a3 * g.z, b.a3 * g.w);
+            if (mask & 1u) gr.red(gp0 + GS * o0, b.a0);
+            if (mask & 2u) gr.red(gp0 + GS * (o0 + csb), b.a1);
+            if (mask & 4u) gr.red(gp0 + GS * o2, b.a2);
+            if (mask & 8u) gr.red(gp0 + GS * (o2 + csb), b.a3);
         }
     }
     pa = fmaf(b.w0, d0, fmaf(b.w1, d1, fmaf(b.w2, d2, fmaf(b.w3, d3, pa))));
@@ -220,15 +402,21 @@ inline int pick_pairs_d48(int configured, int Lq, int M, int nz)
     return ctas < 148 * 3 ? 8 : 16;
 }
 
-// sum over the 4 lanes of a shuffle sub-group (full-warp participation required)
+// sum over the G (= 2 or 4) lanes of a shuffle sub-group (full-warp participation required)
+template <int G>
 __device__ __forceinline__ void subgroup_sum3(float &a, float &b, float &c)
 {
     a += __shfl_xor_sync(0xffffffffu, a, 1);
     b += __shfl_xor_sync(0xffffffffu, b, 1);
     c += __shfl_xor_sync(0xffffffffu, c, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
-    b += __shfl_xor_sync(0xffffffffu, b, 2);
-    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    if (G == 4) {
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        b += __shfl_xor_sync(0xffffffffu, b, 2);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+    }
 }
+
+// lanes per shuffle sub-group for a pair of LANES lanes (pairs never straddle a sub-group)
+constexpr int sub_group(int lanes) { return lanes % 4 == 0 ? 4 : 2; }
 
 }  // namespace msda

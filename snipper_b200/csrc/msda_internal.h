@@ -22,7 +22,17 @@ struct SnippetDims {
 
 // ---- per-call op (msda_percall.cu) ----
 // fast = vectorised fp32 path (D % 16 == 0, D <= 256); generic = any D, float or double.
-bool fast_path_ok(const OpDims &d);
+bool fast_path_ok(const OpDims &d);             // fp32
+bool fast_path_ok(const OpDims &d, int esize);  // esize = 4 (float) or 2 (bf16)
+
+// bf16 value / output / grad_output, fp32 everything else (grad_value accumulates in fp32)
+cudaError_t launch_forward_fast_bf16(const void *value, const int64_t *shapes, const int64_t *lsi,
+                                     const float *loc, const float *attn, void *out,
+                                     const OpDims &d, cudaStream_t stream);
+cudaError_t launch_backward_fast_bf16(const void *value, const int64_t *shapes, const int64_t *lsi,
+                                      const float *loc, const float *attn, const void *grad_out,
+                                      float *grad_value, float *grad_loc, float *grad_attn,
+                                      const OpDims &d, cudaStream_t stream);
 
 cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
                                     const float *loc, const float *attn, float *out,
@@ -52,7 +62,18 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
                                               bool accumulate);
 
 // ---- fused snippet op (msda_snippet.cu) ----
-bool snippet_ok(const SnippetDims &d);
+bool snippet_ok(const SnippetDims &d);             // fp32
+bool snippet_ok(const SnippetDims &d, int esize);
+cudaError_t launch_snippet_forward_bf16(const void *value, const int64_t *shapes,
+                                        const int64_t *lsi, const float *offsets,
+                                        const float *logits, const float *ref, void *out,
+                                        const SnippetDims &d, cudaStream_t stream);
+cudaError_t launch_snippet_backward_bf16(const void *value, const int64_t *shapes,
+                                         const int64_t *lsi, const float *offsets,
+                                         const float *logits, const float *ref,
+                                         const void *grad_out, float *grad_value,
+                                         float *grad_offsets, float *grad_logits,
+                                         const SnippetDims &d, cudaStream_t stream);
 cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes,
                                        const int64_t *lsi, const float *offsets,
                                        const float *logits, const float *ref, float *out,

@@ -24,7 +24,8 @@
 namespace msda {
 
 // ------------------------------------------------------------------------------------------
-// FAST fp32 path (see msda_fast.cuh for the CTA organisation)
+// FAST path (see msda_fast.cuh for the CTA organisation).  VT = element type of value / output /
+// grad_output (float or __nv_bfloat16); loc / attn / grad_loc / grad_attn / grad_value are fp32.
 // ------------------------------------------------------------------------------------------
 // grid = (M, query tiles, N): a CTA owns PAIRS consecutive queries of ONE head.  Consecutive
 // queries are neighbouring pixels in the encoder, so the cells they gather overlap and hit in L1.
@@ -32,30 +33,35 @@ template <int LANES, int PAIRS_>
 struct FastCfg {
     static constexpr int PAIRS = PAIRS_;
     static constexpr int THREADS = PAIRS * LANES;
-    static constexpr int SUBS = LANES / 4;                                 // 4-lane shuffle groups
+    static constexpr int SUBG = sub_group(LANES);                          // lanes per shuffle group
+    static constexpr int SUBS = LANES / SUBG;                              // shuffle groups per pair
     static constexpr int CHUNK = (512 / PAIRS) < 32 ? (512 / PAIRS) : 32;  // samples per query per pass
-    static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
+    static_assert(LANES % 2 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
 int g_fwd_variant = 1;  // msda_set_tuning("fwd_variant", 0|1|2): 1 (two samples per step) measured best, profiles/r01_run9_*
 
 struct FastArgs {
     int M, L, P, Lq, S;
-    int cell_bytes;            // M * D * 4
+    int cell_bytes;            // M * D * sizeof(VT): bytes between consecutive cells of `value`
     int cl;                    // samples per query per pass (<= CHUNK)
     unsigned magic_cl, magic_P;
     int64_t value_batch_stride;  // elements
 };
 
-// VAR (experiments, msda_set_tuning("fwd_variant")): 0 = one sample per step; 1 = two samples per
-// step (gather_fma2); 2 = as 0 with the register cap that admits 10 CTAs per SM.
-template <int LANES, int PAIRS, int CSB, int VAR = 0>
-__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS, VAR == 2 ? 1920 / FastCfg<LANES, PAIRS>::THREADS : (VAR == 1 ? 960 / FastCfg<LANES, PAIRS>::THREADS : 0))
-msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+// VAR (msda_set_tuning("fwd_variant")): 0 = one sample per step; 1 = two samples per step
+// (gather_fma2, default); 2 = as 0 with the register cap that admits 10 CTAs per SM.
+template <typename VT, int LANES, int PAIRS, int CSB, int VAR = 0>
+__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS,
+                                  VAR == 2 ? 1920 / FastCfg<LANES, PAIRS>::THREADS
+                                           : (VAR == 1 ? 960 / FastCfg<LANES, PAIRS>::THREADS : 0))
+msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                     const float *__restrict__ attn, float *__restrict__ out, const FastArgs a)
+                     const float *__restrict__ attn, typename Chunk<VT>::elem *__restrict__ out, const FastArgs a)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
+    using C = Chunk<VT>;
+    using ET = typename C::elem;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *wts = reinterpret_cast<float4 *>(smem_raw);
@@ -73,8 +79,8 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     const bool live = q0 + pl < a.Lq;
     const size_t pair = ((size_t)nb * a.Lq + q0 + pl) * a.M + m;
     const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
-                     (size_t)(m * LANES + lane) * 16;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                     (size_t)(m * LANES + lane) * C::BYTES;
+    C acc = zero_chunk<C>();
 
     for (int lp0 = 0; lp0 < LP; lp0 += a.cl) {
         const int n = min(a.cl, LP - lp0);
@@ -106,29 +112,33 @@ msda_fwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
             if (VAR == 1) {
                 int j = 0;
 #pragma unroll 2
-                for (; j + 1 < n; j += 2) gather_fma2<CSB>(acc, mm[j], ww[j], mm[j + 1], ww[j + 1], p0, a.cell_bytes);
-                if (j < n) gather_fma<CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
+                for (; j + 1 < n; j += 2)
+                    gather_fma2<VT, CSB>(acc, mm[j], ww[j], mm[j + 1], ww[j + 1], p0, a.cell_bytes);
+                if (j < n) gather_fma<VT, CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
             } else {
 #pragma unroll 4
-                for (int j = 0; j < n; ++j) gather_fma<CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
+                for (int j = 0; j < n; ++j) gather_fma<VT, CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
             }
         }
         if (lp0 + a.cl < LP) __syncthreads();  // staging buffers are reused by the next pass
     }
-    if (live) reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
+    if (live) acc.store(reinterpret_cast<char *>(out) + (pair * LANES + lane) * C::BYTES);
 }
 
 // SCATTER == false: grad_sampling_loc / grad_attn_weight only (deterministic mode computes
-// grad_value separately, msda_deterministic.cu)
-template <int LANES, int PAIRS, int CSB, bool SCATTER>
+// grad_value separately, msda_deterministic.cu).  grad_value is fp32 for every VT.
+template <typename VT, int LANES, int PAIRS, int CSB, bool SCATTER>
 __global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
-msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+msda_bwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                     const float *__restrict__ attn, const float *__restrict__ grad_out,
+                     const float *__restrict__ attn, const typename Chunk<VT>::elem *__restrict__ grad_out,
                      float *__restrict__ grad_value, float *__restrict__ grad_loc,
                      float *__restrict__ grad_attn, const FastArgs a)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
+    using C = Chunk<VT>;
+    using ET = typename C::elem;
+    constexpr int GS = 4 / (int)sizeof(ET);
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
@@ -145,14 +155,16 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
 
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
-    const int sub = lane >> 2;
+    const int sub = lane / Cfg::SUBG;
     const bool live = q0 + pl < a.Lq;
     const size_t pair = ((size_t)nb * a.Lq + q0 + pl) * a.M + m;
     const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
-                     (size_t)(m * LANES + lane) * 16;
-    char *gp0 = reinterpret_cast<char *>(grad_value) + ((size_t)nb * a.S * a.cell_bytes) + (size_t)(m * LANES + lane) * 16;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
+                     (size_t)(m * LANES + lane) * C::BYTES;
+    char *gp0 = reinterpret_cast<char *>(grad_value) + ((size_t)nb * a.S * a.cell_bytes + (size_t)m * LANES * C::BYTES) * GS +
+                RedView<VT>::lane_offset(lane);
+    C g = zero_chunk<C>();
+    if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + lane) * C::BYTES);
+    const RedView<VT> gr = RedView<VT>::make(g);
 
     for (int lp0 = 0; lp0 < LP; lp0 += a.cl) {
         const int n = min(a.cl, LP - lp0);
@@ -185,9 +197,9 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
                 const float4 f = ff[j];
                 const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
                 float pa = 0.f, px = 0.f, py = 0.f;
-                gather_scatter<CSB, SCATTER>(mm[j], bw, g, p0, gp0, a.cell_bytes, pa, px, py);
-                subgroup_sum3(pa, px, py);
-                if ((lane & 3) == 0) {
+                gather_scatter<VT, CSB, SCATTER>(mm[j], bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
+                subgroup_sum3<Cfg::SUBG>(pa, px, py);
+                if ((lane & (Cfg::SUBG - 1)) == 0) {
                     float *dst = mypart + j * (Cfg::SUBS * 3);
                     dst[0] = pa; dst[1] = px; dst[2] = py;
                 }
@@ -215,29 +227,37 @@ msda_bwd_fast_kernel(const float *__restrict__ value, const int64_t *__restrict_
     }
 }
 
-bool fast_path_ok(const OpDims &d)
+// esize = sizeof(VT)
+bool fast_path_ok(const OpDims &d, int esize)
 {
-    if (d.D % 16 != 0 || d.D > 128) return false;
+    const int epl = 16 / esize;                    // channels per 16-byte lane
+    if (d.D % epl != 0) return false;
+    const int lanes = d.D / epl;
+    if (lanes % 2 != 0 || lanes > 32) return false;
+    if (esize == 4 && lanes % 4 != 0) return false;  // fp32 instantiations: LANES in {4,8,...,32}
+    if (esize == 2 && lanes != 2 && lanes != 4 && lanes != 6 && lanes != 8 && lanes != 12 && lanes != 16) return false;
     if (d.L > kMaxLevels) return false;
-    if (d.value_batch_stride % 4 != 0) return false;
+    if ((d.value_batch_stride * esize) % 16 != 0) return false;
     // 28-bit row stride / 31-bit cell offsets in bytes (SampleMeta)
-    if ((int64_t)d.S * d.M * d.D * 4 >= ((int64_t)1 << 28)) return false;
+    if ((int64_t)d.S * d.M * d.D * esize >= ((int64_t)1 << 28)) return false;
     // grid dimensions (y: query tiles, z: batch) and the 24-bit fast_div range
     if (d.N > 65535 || (d.Lq + 7) / 8 > 65535) return false;
     if ((int64_t)d.L * d.P >= 4096) return false;
     return true;
 }
 
+bool fast_path_ok(const OpDims &d) { return fast_path_ok(d, 4); }
+
 int g_pairs_d48 = 16;  // queries per CTA tile for LANES == 12 (msda_set_tuning("pairs_d48", 8|16|32))
 
-template <int LANES, int PAIRS>
-static FastArgs make_fast_args(const OpDims &d)
+template <typename VT, int LANES, int PAIRS>
+static FastArgs make_fast_args(const OpDims &d)  // VT = lane type (float, __nv_bfloat16, bf16q)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
     const int LP = d.L * d.P;
     FastArgs a;
     a.M = d.M; a.L = d.L; a.P = d.P; a.Lq = d.Lq; a.S = d.S;
-    a.cell_bytes = d.M * d.D * 4;
+    a.cell_bytes = d.M * d.D * (int)sizeof(typename Chunk<VT>::elem);
     a.cl = LP < Cfg::CHUNK ? LP : Cfg::CHUNK;
     a.magic_cl = fast_magic(a.cl);
     a.magic_P = fast_magic(d.P);
@@ -245,63 +265,81 @@ static FastArgs make_fast_args(const OpDims &d)
     return a;
 }
 
-template <int LANES, int PAIRS>
-static cudaError_t launch_fwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
-                                   const float *loc, const float *attn, float *out,
+// Snipper's cell stride (M*D = 384 elements) becomes an immediate offset in the gather
+template <typename VT, int LANES>
+constexpr int snipper_csb() { return (LANES * Chunk<VT>::N == 48) ? 384 * (int)sizeof(typename Chunk<VT>::elem) : 0; }
+
+template <typename VT, int LANES, int PAIRS>
+static cudaError_t launch_fwd_fast(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
+                                   const float *loc, const float *attn, typename Chunk<VT>::elem *out,
                                    const OpDims &d, cudaStream_t stream)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
-    const FastArgs a = make_fast_args<LANES, PAIRS>(d);
+    const FastArgs a = make_fast_args<VT, LANES, PAIRS>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) + sizeof(SampleMeta) * Cfg::PAIRS * a.cl;
-    if (LANES == 12 && d.M == 8) {  // Snipper: cell stride 1536 B becomes an immediate offset
-        constexpr int C = LANES == 12 ? 1536 : 0;
+    constexpr int C = snipper_csb<VT, LANES>();
+    if (C != 0 && d.M * d.D == 384) {
         if (g_fwd_variant == 1)
-            msda_fwd_fast_kernel<LANES, PAIRS, C, (LANES == 12 ? 1 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+            msda_fwd_fast_kernel<VT, LANES, PAIRS, C, (C != 0 ? 1 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
         else if (g_fwd_variant == 2)
-            msda_fwd_fast_kernel<LANES, PAIRS, C, (LANES == 12 ? 2 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+            msda_fwd_fast_kernel<VT, LANES, PAIRS, C, (C != 0 ? 2 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
         else
-            msda_fwd_fast_kernel<LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+            msda_fwd_fast_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
     } else
-        msda_fwd_fast_kernel<LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+        msda_fwd_fast_kernel<VT, LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
     return cudaGetLastError();
 }
 
-template <int LANES, int PAIRS, bool SCATTER = true>
-static cudaError_t launch_bwd_fast(const float *value, const int64_t *shapes, const int64_t *lsi,
-                                   const float *loc, const float *attn, const float *grad_out,
+template <typename VT, int LANES, int PAIRS, bool SCATTER = true>
+static cudaError_t launch_bwd_fast(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
+                                   const float *loc, const float *attn, const typename Chunk<VT>::elem *grad_out,
                                    float *grad_value, float *grad_loc, float *grad_attn,
                                    const OpDims &d, cudaStream_t stream)
 {
     using Cfg = FastCfg<LANES, PAIRS>;
-    const FastArgs a = make_fast_args<LANES, PAIRS>(d);
+    const FastArgs a = make_fast_args<VT, LANES, PAIRS>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) +
                         (sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * a.cl;
-    if (LANES == 12 && d.M == 8)
-        msda_bwd_fast_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0), SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
+    constexpr int C = snipper_csb<VT, LANES>();
+    if (C != 0 && d.M * d.D == 384)
+        msda_bwd_fast_kernel<VT, LANES, PAIRS, C, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
     else
-        msda_bwd_fast_kernel<LANES, PAIRS, 0, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
+        msda_bwd_fast_kernel<VT, LANES, PAIRS, 0, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
     return cudaGetLastError();
 }
 
+// fp32: LANES = D/4 in {4,...,32}; Snipper's D = 48 (12 lanes) has a tunable tile length
 #define MSDA_DISPATCH_LANES(D, CALL)                                  \
     switch ((D) / 4) {                                                \
-        case 4: return CALL(4, 16);                                   \
-        case 8: return CALL(8, 16);                                   \
+        case 4: return CALL(float, 4, 16);                            \
+        case 8: return CALL(float, 8, 16);                            \
         case 12: {                                                    \
             const int pairs_ = pick_pairs_d48(g_pairs_d48, d.Lq, d.M, d.N); \
-            if (pairs_ == 8) return CALL(12, 8);                      \
-            if (pairs_ == 32) return CALL(12, 32);                    \
-            return CALL(12, 16);                                      \
+            if (pairs_ == 8) return CALL(float, 12, 8);               \
+            if (pairs_ == 32) return CALL(float, 12, 32);             \
+            return CALL(float, 12, 16);                               \
         }                                                             \
-        case 16: return CALL(16, 16);                                 \
-        case 20: return CALL(20, 16);                                 \
-        case 24: return CALL(24, 16);                                 \
-        case 28: return CALL(28, 16);                                 \
-        case 32: return CALL(32, 16);                                 \
+        case 16: return CALL(float, 16, 16);                          \
+        case 20: return CALL(float, 20, 16);                          \
+        case 24: return CALL(float, 24, 16);                          \
+        case 28: return CALL(float, 28, 16);                          \
+        case 32: return CALL(float, 32, 16);                          \
+        default: return cudaErrorInvalidValue;                        \
+    }
+
+// bf16: LANES = D/8; 16 queries x 6 lanes = 96 threads for Snipper's D = 48
+#define MSDA_DISPATCH_LANES_BF16(D, CALL)                             \
+    switch ((D) / 8) {                                                \
+        case 2: return CALL(__nv_bfloat16, 2, 16);                    \
+        case 4: return CALL(__nv_bfloat16, 4, 16);                    \
+        case 6: return CALL(__nv_bfloat16, 6, 16);                    \
+        case 8: return CALL(__nv_bfloat16, 8, 16);                    \
+        case 12: return CALL(__nv_bfloat16, 12, 16);                  \
+        case 16: return CALL(__nv_bfloat16, 16, 16);                  \
         default: return cudaErrorInvalidValue;                        \
     }
 
@@ -310,7 +348,7 @@ cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, c
                                     const OpDims &d, cudaStream_t stream)
 {
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
-#define CALL(LN, PR) launch_fwd_fast<LN, PR>(value, shapes, lsi, loc, attn, out, d, stream)
+#define CALL(VT, LN, PR) launch_fwd_fast<VT, LN, PR>(value, shapes, lsi, loc, attn, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }
@@ -321,8 +359,35 @@ cudaError_t launch_backward_fast_f32(const float *value, const int64_t *shapes, 
                                      const OpDims &d, cudaStream_t stream)
 {
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
-#define CALL(LN, PR) \
-    launch_bwd_fast<LN, PR>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d, stream)
+#define CALL(VT, LN, PR) \
+    launch_bwd_fast<VT, LN, PR>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_forward_fast_bf16(const void *value_, const int64_t *shapes, const int64_t *lsi,
+                                     const float *loc, const float *attn, void *out_,
+                                     const OpDims &d, cudaStream_t stream)
+{
+    if (d.N * d.Lq * d.M == 0) return cudaSuccess;
+    const __nv_bfloat16 *value = static_cast<const __nv_bfloat16 *>(value_);
+    __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(out_);
+#define CALL(VT, LN, PR) launch_fwd_fast<VT, LN, PR>(value, shapes, lsi, loc, attn, out, d, stream)
+    MSDA_DISPATCH_LANES_BF16(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_backward_fast_bf16(const void *value_, const int64_t *shapes, const int64_t *lsi,
+                                      const float *loc, const float *attn, const void *grad_out_,
+                                      float *grad_value, float *grad_loc, float *grad_attn,
+                                      const OpDims &d, cudaStream_t stream)
+{
+    if (d.N * d.Lq * d.M == 0) return cudaSuccess;
+    const __nv_bfloat16 *value = static_cast<const __nv_bfloat16 *>(value_);
+    const __nv_bfloat16 *grad_out = static_cast<const __nv_bfloat16 *>(grad_out_);
+    // backward lanes are 8 bytes = 4 channels (bf16q): same lane count and reduction pattern as fp32
+#define CALL(VT, LN, PR) \
+    launch_bwd_fast<bf16q, LN, PR>(value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }
@@ -482,8 +547,8 @@ cudaError_t launch_backward_no_scatter_f32(const float *value, const int64_t *sh
     const bool vec_ok = (reinterpret_cast<uintptr_t>(value) & 15u) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0;
     if (fast_path_ok(d) && vec_ok) {
         float *none = nullptr;
-#define CALL(LN, PR) \
-    launch_bwd_fast<LN, PR, false>(value, shapes, lsi, loc, attn, grad_out, none, grad_loc, grad_attn, d, stream)
+#define CALL(VT, LN, PR) \
+    launch_bwd_fast<VT, LN, PR, false>(value, shapes, lsi, loc, attn, grad_out, none, grad_loc, grad_attn, d, stream)
         MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
     }

@@ -28,16 +28,17 @@ template <int LANES, int PAIRS_>
 struct SnipCfg {
     static constexpr int PAIRS = PAIRS_;
     static constexpr int THREADS = PAIRS * LANES;
-    static constexpr int SUBS = LANES / 4;
+    static constexpr int SUBG = sub_group(LANES);
+    static constexpr int SUBS = LANES / SUBG;
     // register caps: >= 1152 resident threads/SM forward (<= 56 regs), >= 768 backward (<= 80 regs)
-    static constexpr int FWD_MIN_BLOCKS = 1152 / THREADS < 1 ? 1 : 1152 / THREADS;
-    static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : 768 / THREADS;
-    static_assert(LANES % 4 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
+    static constexpr int FWD_MIN_BLOCKS = 1152 / THREADS < 1 ? 1 : (1152 / THREADS > 16 ? 16 : 1152 / THREADS);
+    static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : (768 / THREADS > 16 ? 16 : 768 / THREADS);
+    static_assert(LANES % 2 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
 struct SnipArgs {
     SnippetDims d;
-    int cell_bytes;            // M * D * 4
+    int cell_bytes;            // M * D * sizeof(VT)
     unsigned magic_LP, magic_P;
 };
 
@@ -107,14 +108,16 @@ __device__ __forceinline__ void snippet_phase1(SampleMeta *meta, float4 *second,
     __syncthreads();
 }
 
-template <int LANES, int PAIRS, int CSB>
+template <typename VT, int LANES, int PAIRS, int CSB>
 __global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::FWD_MIN_BLOCKS)
-msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
-                        float *__restrict__ out, const SnipArgs a)
+                        typename Chunk<VT>::elem *__restrict__ out, const SnipArgs a)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
+    using C = Chunk<VT>;
+    using ET = typename C::elem;
     const SnippetDims &d = a.d;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,25 +147,28 @@ msda_snippet_fwd_kernel(const float *__restrict__ value, const int64_t *__restri
     if (q0 + pl >= d.Lq) return;
     const size_t pair = (qbase + q0 + pl) * d.M + m;
     const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
-                     (size_t)(m * LANES + lane) * 16;
-    const int64_t fstride = d.value_stride_t * 4;  // bytes between frames
+                     (size_t)(m * LANES + lane) * C::BYTES;
+    const int64_t fstride = d.value_stride_t * (int64_t)sizeof(ET);  // bytes between frames
     const SampleMeta *mm = meta + pl * LP;
     const float4 *ww = wts + pl * (LP + 1);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < LP; ++j) gather_fma_frames<CSB>(acc, mm[j], ww[j], pf, fstride, nf, a.cell_bytes);
-    reinterpret_cast<float4 *>(out)[pair * LANES + lane] = acc;
+    C acc = zero_chunk<C>();
+    for (int j = 0; j < LP; ++j) gather_fma_frames<VT, CSB>(acc, mm[j], ww[j], pf, fstride, nf, a.cell_bytes);
+    acc.store(reinterpret_cast<char *>(out) + (pair * LANES + lane) * C::BYTES);
 }
 
-template <int LANES, int PAIRS, int CSB>
+template <typename VT, int LANES, int PAIRS, int CSB>
 __global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS)
-msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
-                        const float *__restrict__ grad_out, float *__restrict__ grad_value,
+                        const typename Chunk<VT>::elem *__restrict__ grad_out, float *__restrict__ grad_value,
                         float *__restrict__ grad_offsets, float *__restrict__ grad_logits,
                         const SnipArgs a)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
+    using C = Chunk<VT>;
+    using ET = typename C::elem;
+    constexpr int GS = 4 / (int)sizeof(ET);
     const SnippetDims &d = a.d;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -191,17 +197,20 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     {
         const int pl = tid / LANES;
         const int lane = tid - pl * LANES;
-        const int sub = lane >> 2;
+        const int sub = lane / Cfg::SUBG;
         const bool live = q0 + pl < d.Lq;
         const size_t pair = (qbase + q0 + pl) * d.M + m;
         const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
-                         (size_t)(m * LANES + lane) * 16;
-        char *gpf = reinterpret_cast<char *>(grad_value) + ((size_t)n * d.T2 + lo) * d.S * a.cell_bytes +
-                    (size_t)(m * LANES + lane) * 16;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) g = ldg4(reinterpret_cast<const float4 *>(grad_out) + pair * LANES + lane);
-        const int64_t fstride = d.value_stride_t * 4;
-        const int64_t gfstride = (int64_t)d.S * a.cell_bytes;
+                         (size_t)(m * LANES + lane) * C::BYTES;
+        // grad_value is a dense fp32 (N,T2,S,M,D) buffer: GS x the value byte offsets
+        char *gpf = reinterpret_cast<char *>(grad_value) +
+                    (((size_t)n * d.T2 + lo) * d.S * a.cell_bytes + (size_t)m * LANES * C::BYTES) * GS +
+                    RedView<VT>::lane_offset(lane);
+        C g = zero_chunk<C>();
+        if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + lane) * C::BYTES);
+        const RedView<VT> gr = RedView<VT>::make(g);
+        const int64_t fstride = d.value_stride_t * (int64_t)sizeof(ET);
+        const int64_t gfstride = (int64_t)d.S * a.cell_bytes * GS;
         const SampleMeta *mm = meta + pl * LP;
         const float4 *ff = frac + pl * (LP + 1);
         float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
@@ -213,10 +222,10 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
             const char *p0 = pf;
             char *gp0 = gpf;
             for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
-                gather_scatter<CSB, true>(mt, bw, g, p0, gp0, a.cell_bytes, pa, px, py);
-            subgroup_sum3(pa, px, py);
+                gather_scatter<VT, CSB, true>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
+            subgroup_sum3<Cfg::SUBG>(pa, px, py);
             // zs/es alias `part`: all phase-1 reads finished at the barrier that ends phase 1
-            if ((lane & 3) == 0) {
+            if ((lane & (Cfg::SUBG - 1)) == 0) {
                 float *dst = mypart + j * (Cfg::SUBS * 3);
                 dst[0] = pa; dst[1] = px; dst[2] = py;
             }
@@ -257,93 +266,117 @@ msda_snippet_bwd_kernel(const float *__restrict__ value, const int64_t *__restri
     }
 }
 
-bool snippet_ok(const SnippetDims &d)
+bool snippet_ok(const SnippetDims &d, int esize)
 {
-    if (d.D % 16 != 0 || d.D > 128) return false;
+    const int epl = 16 / esize;
+    if (d.D % epl != 0) return false;
+    const int lanes = d.D / epl;
+    if (esize == 4 && (lanes % 4 != 0 || lanes > 32)) return false;
+    if (esize == 2 && lanes != 2 && lanes != 4 && lanes != 6 && lanes != 8 && lanes != 12 && lanes != 16) return false;
     if (d.L > kMaxLevels || d.L * d.P > kSnippetMaxLP) return false;
-    if (d.value_stride_n % 4 != 0 || d.value_stride_t % 4 != 0) return false;
-    if ((int64_t)d.S * d.M * d.D * 4 >= ((int64_t)1 << 28)) return false;  // SampleMeta bit budget
+    if ((d.value_stride_n * esize) % 16 != 0 || (d.value_stride_t * esize) % 16 != 0) return false;
+    if ((int64_t)d.S * d.M * d.D * esize >= ((int64_t)1 << 28)) return false;  // SampleMeta bit budget
     if ((int64_t)d.N * d.T1 > 65535 || (d.Lq + 7) / 8 > 65535) return false;
     return true;
 }
 
+bool snippet_ok(const SnippetDims &d) { return snippet_ok(d, 4); }
+
 int g_snip_pairs_d48 = 16;  // msda_set_tuning("snip_pairs_d48", 8|16|32)
 
+template <typename VT>
 static SnipArgs make_snip_args(const SnippetDims &d)
 {
     SnipArgs a;
     a.d = d;
-    a.cell_bytes = d.M * d.D * 4;
+    a.cell_bytes = d.M * d.D * (int)sizeof(typename Chunk<VT>::elem);
     a.magic_LP = fast_magic(d.L * d.P);
     a.magic_P = fast_magic(d.P);
     return a;
 }
 
-template <int LANES, int PAIRS>
-static cudaError_t launch_snip_fwd(const float *value, const int64_t *shapes, const int64_t *lsi,
+// Snipper's cell stride (M*D = 384 elements) as an immediate offset
+template <typename VT, int LANES>
+constexpr int snip_csb() { return (LANES * Chunk<VT>::N == 48) ? 384 * (int)sizeof(typename Chunk<VT>::elem) : 0; }
+
+template <typename VT, int LANES, int PAIRS>
+static cudaError_t launch_snip_fwd(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *offsets, const float *logits, const float *ref,
-                                   float *out, const SnippetDims &d, cudaStream_t stream)
+                                   typename Chunk<VT>::elem *out, const SnippetDims &d, cudaStream_t stream)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
-    const SnipArgs a = make_snip_args(d);
+    const SnipArgs a = make_snip_args<VT>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) +
                         (sizeof(SampleMeta) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
-    if (LANES == 12 && d.M == 8)
-        msda_snippet_fwd_kernel<LANES, PAIRS, (LANES == 12 ? 1536 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(
+    constexpr int C = snip_csb<VT, LANES>();
+    if (C != 0 && d.M * d.D == 384)
+        msda_snippet_fwd_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, offsets, logits, ref, out, a);
     else
-        msda_snippet_fwd_kernel<LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets,
-                                                                                    logits, ref, out, a);
+        msda_snippet_fwd_kernel<VT, LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(
+            value, shapes, lsi, offsets, logits, ref, out, a);
     return cudaGetLastError();
 }
 
-template <int LANES, int PAIRS, int CSB>
-static cudaError_t launch_snip_bwd_impl(const float *value, const int64_t *shapes, const int64_t *lsi,
+template <typename VT, int LANES, int PAIRS, int CSB>
+static cudaError_t launch_snip_bwd_impl(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
                                         const float *offsets, const float *logits, const float *ref,
-                                        const float *grad_out, float *grad_value, float *grad_offsets,
+                                        const typename Chunk<VT>::elem *grad_out, float *grad_value, float *grad_offsets,
                                         float *grad_logits, const SnippetDims &d, cudaStream_t stream)
 {
     using Cfg = SnipCfg<LANES, PAIRS>;
-    const SnipArgs a = make_snip_args(d);
+    const SnipArgs a = make_snip_args<VT>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) +
                         (sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(msda_snippet_bwd_kernel<LANES, PAIRS, CSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    msda_snippet_bwd_kernel<LANES, PAIRS, CSB><<<grid, Cfg::THREADS, smem, stream>>>(
+        cudaFuncSetAttribute(msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB><<<grid, Cfg::THREADS, smem, stream>>>(
         value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, a);
     return cudaGetLastError();
 }
 
-template <int LANES, int PAIRS>
-static cudaError_t launch_snip_bwd(const float *value, const int64_t *shapes, const int64_t *lsi,
+template <typename VT, int LANES, int PAIRS>
+static cudaError_t launch_snip_bwd(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
                                    const float *offsets, const float *logits, const float *ref,
-                                   const float *grad_out, float *grad_value, float *grad_offsets,
+                                   const typename Chunk<VT>::elem *grad_out, float *grad_value, float *grad_offsets,
                                    float *grad_logits, const SnippetDims &d, cudaStream_t stream)
 {
-    if (LANES == 12 && d.M == 8)
-        return launch_snip_bwd_impl<LANES, PAIRS, (LANES == 12 ? 1536 : 0)>(value, shapes, lsi, offsets, logits, ref, grad_out,
-                                                                         grad_value, grad_offsets, grad_logits, d, stream);
-    return launch_snip_bwd_impl<LANES, PAIRS, 0>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value,
-                                                 grad_offsets, grad_logits, d, stream);
+    constexpr int C = snip_csb<VT, LANES>();
+    if (C != 0 && d.M * d.D == 384)
+        return launch_snip_bwd_impl<VT, LANES, PAIRS, C>(value, shapes, lsi, offsets, logits, ref, grad_out,
+                                                         grad_value, grad_offsets, grad_logits, d, stream);
+    return launch_snip_bwd_impl<VT, LANES, PAIRS, 0>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value,
+                                                     grad_offsets, grad_logits, d, stream);
 }
 
 #define MSDA_DISPATCH_LANES(D, CALL)                                  \
     switch ((D) / 4) {                                                \
-        case 4: return CALL(4, 16);                                   \
-        case 8: return CALL(8, 16);                                   \
+        case 4: return CALL(float, 4, 16);                            \
+        case 8: return CALL(float, 8, 16);                            \
         case 12: {                                                    \
             const int pairs_ = pick_pairs_d48(g_snip_pairs_d48, d.Lq, d.M, d.N * d.T1); \
-            if (pairs_ == 8) return CALL(12, 8);                      \
-            if (pairs_ == 32) return CALL(12, 32);                    \
-            return CALL(12, 16);                                      \
+            if (pairs_ == 8) return CALL(float, 12, 8);               \
+            if (pairs_ == 32) return CALL(float, 12, 32);             \
+            return CALL(float, 12, 16);                               \
         }                                                             \
-        case 16: return CALL(16, 16);                                 \
-        case 20: return CALL(20, 8);                                  \
-        case 24: return CALL(24, 8);                                  \
-        case 28: return CALL(28, 8);                                  \
-        case 32: return CALL(32, 8);                                  \
+        case 16: return CALL(float, 16, 16);                          \
+        case 20: return CALL(float, 20, 8);                           \
+        case 24: return CALL(float, 24, 8);                           \
+        case 28: return CALL(float, 28, 8);                           \
+        case 32: return CALL(float, 32, 8);                           \
+        default: return cudaErrorInvalidValue;                        \
+    }
+
+#define MSDA_DISPATCH_LANES_BF16(D, CALL)                             \
+    switch ((D) / 8) {                                                \
+        case 2: return CALL(__nv_bfloat16, 2, 16);                    \
+        case 4: return CALL(__nv_bfloat16, 4, 16);                    \
+        case 6: return CALL(__nv_bfloat16, 6, 16);                    \
+        case 8: return CALL(__nv_bfloat16, 8, 16);                    \
+        case 12: return CALL(__nv_bfloat16, 12, 16);                  \
+        case 16: return CALL(__nv_bfloat16, 16, 8);                   \
         default: return cudaErrorInvalidValue;                        \
     }
 
@@ -352,7 +385,7 @@ cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes
                                        const float *logits, const float *ref, float *out,
                                        const SnippetDims &d, cudaStream_t stream)
 {
-#define CALL(LN, PR) launch_snip_fwd<LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
+#define CALL(VT, LN, PR) launch_snip_fwd<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }
@@ -364,8 +397,36 @@ cudaError_t launch_snippet_backward_f32(const float *value, const int64_t *shape
                                         float *grad_offsets, float *grad_logits,
                                         const SnippetDims &d, cudaStream_t stream)
 {
-#define CALL(LN, PR) \
-    launch_snip_bwd<LN, PR>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
+#define CALL(VT, LN, PR) \
+    launch_snip_bwd<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_snippet_forward_bf16(const void *value_, const int64_t *shapes,
+                                        const int64_t *lsi, const float *offsets,
+                                        const float *logits, const float *ref, void *out_,
+                                        const SnippetDims &d, cudaStream_t stream)
+{
+    const __nv_bfloat16 *value = static_cast<const __nv_bfloat16 *>(value_);
+    __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(out_);
+#define CALL(VT, LN, PR) launch_snip_fwd<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
+    MSDA_DISPATCH_LANES_BF16(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_snippet_backward_bf16(const void *value_, const int64_t *shapes,
+                                         const int64_t *lsi, const float *offsets,
+                                         const float *logits, const float *ref,
+                                         const void *grad_out_, float *grad_value,
+                                         float *grad_offsets, float *grad_logits,
+                                         const SnippetDims &d, cudaStream_t stream)
+{
+    const __nv_bfloat16 *value = static_cast<const __nv_bfloat16 *>(value_);
+    const __nv_bfloat16 *grad_out = static_cast<const __nv_bfloat16 *>(grad_out_);
+    // backward lanes are 8 bytes = 4 channels (bf16q): same lane count and reduction pattern as fp32
+#define CALL(VT, LN, PR) \
+    launch_snip_bwd<bf16q, LN, PR>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
 }

@@ -90,12 +90,12 @@ class MSDeformAttn(nn.Module):
         so, aw = self.sampling_offsets, self.attention_weights
         return all(m is so[0] for m in so) and all(m is aw[0] for m in aw)
 
-    def _can_fuse(self, query):
+    def _can_fuse(self, value):
         if ops.is_deterministic() and torch.is_grad_enabled():
             return False  # the deterministic grad_value path lives in the per-call backward
-        return (self.fused and self._slots_aliased() and query.is_cuda and
+        return (self.fused and self._slots_aliased() and value.is_cuda and
                 ops.snippet_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
-                                      self.n_points, query.dtype))
+                                      self.n_points, value.dtype))
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
                 input_level_start_index, input_padding_mask=None):
@@ -112,12 +112,14 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask, 0.0)
         value = value.view(N, T2, S, M, self.d_model // M)
 
-        if self._can_fuse(query):
-            offsets = self.sampling_offsets[0](query).view(N, T1, Lq, M, L, P, 2)
-            logits = self.attention_weights[0](query).view(N, T1, Lq, M, L, P)
+        if self._can_fuse(value):
+            # value may be bf16 (autocast): the kernels gather bf16 and keep every location /
+            # weight computation in fp32, so offsets, logits and reference points go in as fp32
+            offsets = self.sampling_offsets[0](query).float().view(N, T1, Lq, M, L, P, 2)
+            logits = self.attention_weights[0](query).float().view(N, T1, Lq, M, L, P)
             out = torch.ops.snipper_b200.snippet_forward(
                 value, input_spatial_shapes, input_level_start_index, offsets, logits,
-                reference_points, self.n_frame)
+                reference_points.float(), self.n_frame)
             vis = self._vis_fused(offsets, logits, reference_points, input_spatial_shapes, T2) \
                 if self.attention_vis else None
         else:
@@ -155,10 +157,14 @@ class MSDeformAttn(nn.Module):
             q = query[:, t1]
             logits = torch.stack([self.attention_weights[t2](q).view(N, Lq, M, L, P) for t2 in frames], -1)
             att = F.softmax(logits.flatten(-3), -1).view(N, Lq, M, L, P, len(frames))
+            if value.dtype == torch.bfloat16:
+                att = att.float()
             acc, locs = None, []
             for j, t2 in enumerate(frames):
                 off = self.sampling_offsets[t2](q).view(N, Lq, M, L, P, 2)
                 loc = reference_points[:, t1, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+                if value.dtype == torch.bfloat16:
+                    loc = loc.float()
                 if self.attention_vis:
                     locs.append(loc.detach())
                 # value[:, t2] keeps its batch stride (no copy); loc/att slices are materialised

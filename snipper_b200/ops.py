@@ -18,7 +18,8 @@ from torch import Tensor
 
 from . import capi
 
-_DTYPES = {torch.float32: capi.MSDA_DTYPE_F32, torch.float64: capi.MSDA_DTYPE_F64}
+_DTYPES = {torch.float32: capi.MSDA_DTYPE_F32, torch.float64: capi.MSDA_DTYPE_F64,
+           torch.bfloat16: capi.MSDA_DTYPE_BF16}
 
 # process-wide switch for the deterministic (atomics-free) grad_value path
 _deterministic = False
@@ -116,8 +117,14 @@ def _check_percall(value, spatial_shapes, level_start_index, sampling_loc, attn_
     if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
         raise RuntimeError("expected value (N,S,M,D), sampling_loc (N,Lq,M,L,P,2), attn_weight (N,Lq,M,L,P)")
     if value.dtype not in _DTYPES:
-        raise RuntimeError("ms_deform_attn: unsupported dtype %s (float32 / float64)" % value.dtype)
-    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("ms_deform_attn: unsupported dtype %s (float32 / float64 / bfloat16)" % value.dtype)
+    if value.dtype == torch.bfloat16:
+        # bf16 mode: value / output / grad_output are bf16; locations and weights are computed in fp32
+        if sampling_loc.dtype != torch.float32 or attn_weight.dtype != torch.float32:
+            raise RuntimeError("bfloat16 value needs float32 sampling_loc and attn_weight")
+        if value.shape[3] % 16 != 0 or value.shape[3] > 128:
+            raise RuntimeError("bfloat16 ms_deform_attn needs head channels D % 16 == 0 and D <= 128")
+    elif sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
         raise RuntimeError("value, sampling_loc and attn_weight must share one dtype")
     if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
         raise RuntimeError("spatial_shapes and level_start_index must be int64")
@@ -161,7 +168,11 @@ def msda_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tens
     if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
         raise RuntimeError("grad_output must be (N,Lq,M*D) in value's dtype")
     vbs = _value_batch_stride(value)
-    grad_value = torch.empty((N, S, M, D), dtype=value.dtype, device=value.device)
+    bf16 = value.dtype == torch.bfloat16
+    if bf16 and deterministic:
+        raise RuntimeError("the deterministic backward is float32 only")
+    # bf16 mode accumulates grad_value in fp32 (include/msda_b200.h) and rounds once at the end
+    grad_value = torch.empty((N, S, M, D), dtype=torch.float32 if bf16 else value.dtype, device=value.device)
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
     flags = capi.MSDA_FLAG_DETERMINISTIC if deterministic else 0
@@ -180,6 +191,8 @@ def msda_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tens
             N, S, M, D, L, Lq, P, vbs, int(im2col_step), dt, flags, ws_ptr, ws_bytes,
             _stream(value.device))
     capi.check(st, "ms_deform_attn_backward", N, im2col_step)
+    if bf16:
+        grad_value = grad_value.to(torch.bfloat16)
     return grad_value, grad_loc, grad_attn
 
 
@@ -210,7 +223,7 @@ msda_forward.register_autograd(_msda_backward_formula, setup_context=_msda_setup
 # ------------------------------------------------------------------------------------------
 def snippet_supported(n_heads: int, d_head: int, n_levels: int, n_points: int, dtype) -> bool:
     """Shapes the fused kernels cover (include/msda_b200.h, msda_snippet_forward)."""
-    return (dtype == torch.float32 and d_head % 16 == 0 and d_head <= 128 and
+    return (dtype in (torch.float32, torch.bfloat16) and d_head % 16 == 0 and d_head <= 128 and
             n_levels * n_points <= 32 and n_levels <= 64)
 
 
@@ -228,7 +241,7 @@ def _check_snippet(value, spatial_shapes, level_start_index, offsets, logits, re
     if tuple(ref.shape) != (N, T1, Lq, L, 2) or tuple(spatial_shapes.shape) != (L, 2):
         raise RuntimeError("reference_points must be (N,T1,Lq,L,2) and spatial_shapes (L,2)")
     if not snippet_supported(M, D, L, P, value.dtype):
-        raise RuntimeError("fused snippet attention needs float32, D % 16 == 0, D <= 128, L*P <= 32")
+        raise RuntimeError("fused snippet attention needs float32 / bfloat16 value, D % 16 == 0, D <= 128, L*P <= 32")
     if any(t.dtype != torch.float32 for t in (offsets, logits, ref)):
         raise RuntimeError("offsets, logits and reference_points must be float32")
     if not (0 < n_frame <= T2):
@@ -270,7 +283,7 @@ def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Te
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), out.data_ptr(),
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
-            capi.MSDA_DTYPE_F32, _stream(value.device))
+            _DTYPES[value.dtype], _stream(value.device))
     capi.check(status, "msda_snippet_forward")
     return out
 
@@ -291,7 +304,7 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
     _require_contiguous(grad_output, "grad_output")
     sn, st = _value_strides5(value)
     ref, rsn, rst = _ref_strides(reference_points)
-    grad_value = torch.empty((N, T2, S, M, D), dtype=value.dtype, device=value.device)
+    grad_value = torch.empty((N, T2, S, M, D), dtype=torch.float32, device=value.device)  # fp32 accumulation
     grad_offsets = torch.empty_like(offsets)
     grad_logits = torch.empty_like(logits)
     with torch.cuda.device(value.device), _Launch("snippet_backward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
@@ -300,8 +313,10 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(),
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
-            capi.MSDA_DTYPE_F32, 0, _stream(value.device))
+            _DTYPES[value.dtype], 0, _stream(value.device))
     capi.check(status, "msda_snippet_backward")
+    if value.dtype != torch.float32:
+        grad_value = grad_value.to(value.dtype)
     return grad_value, grad_offsets, grad_logits
 
 

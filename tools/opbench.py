@@ -103,34 +103,40 @@ def time_fn(fn, iters, flush, inner=None):
     return times[len(times) // 2], times[0]
 
 
-def direct_calls(value, shapes, lsi, loc, attn, go):
+def direct_calls(value, shapes, lsi, loc, attn, go, bf16=False):
     """Forward/backward closures that call the C ABI directly (ctypes), bypassing the torch
     custom-op dispatcher (~30 us of host time per call, which would hide a 20 us kernel)."""
     from snipper_b200 import capi
     L = capi.lib()
     N, S, M, D = value.shape
     _, Lq, _, Lv, P, _ = loc.shape
-    out = torch.empty(N, Lq, M * D, device=value.device)
-    gv, gl, ga = torch.empty_like(value), torch.empty_like(loc), torch.empty_like(attn)
+    dt = 2 if bf16 else 0
+    if bf16:
+        value, go = value.bfloat16(), go.bfloat16()
+    out = torch.empty(N, Lq, M * D, device=value.device, dtype=value.dtype)
+    gv, gl, ga = torch.empty(value.shape, device=value.device), torch.empty_like(loc), torch.empty_like(attn)
     st = torch.cuda.current_stream().cuda_stream
-    keep = (out, gv, gl, ga)
+    keep = (out, gv, gl, ga, value, go)
 
     def fwd():
         r = L.msda_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
-                           out.data_ptr(), N, S, M, D, Lv, Lq, P, 0, 64, 0, st)
+                           out.data_ptr(), N, S, M, D, Lv, Lq, P, 0, 64, dt, st)
         assert r == 0, r
 
     def bwd():
         r = L.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                             go.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), N, S, M, D, Lv, Lq, P,
-                            0, 64, 0, 0, 0, 0, st)
+                            0, 64, dt, 0, 0, 0, st)
         assert r == 0, r
 
     def bwd_nomemset():
         r = L.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                             go.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), N, S, M, D, Lv, Lq, P,
-                            0, 64, 0, capi.MSDA_FLAG_ACCUMULATE_VALUE, 0, 0, st)
+                            0, 64, dt, capi.MSDA_FLAG_ACCUMULATE_VALUE, 0, 0, st)
         assert r == 0, r
+
+    if bf16:
+        return fwd, bwd, bwd_nomemset, None, keep
 
     ws_bytes = L.msda_backward_workspace_bytes(N, S, M, D, Lv, Lq, P, 0, capi.MSDA_FLAG_DETERMINISTIC)
     ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=value.device)
@@ -145,7 +151,8 @@ def direct_calls(value, shapes, lsi, loc, attn, go):
     return fwd, bwd, bwd_nomemset, bwd_det, keep + (ws,)
 
 
-def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encoder=True, seed=0, regime="local"):
+def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encoder=True, seed=0, regime="local",
+                  bf16=False):
     """Closures timing the fused per-layer entry points directly through the C ABI."""
     from snipper_b200 import capi
     L = capi.lib()
@@ -174,8 +181,11 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
     else:
         ref = torch.rand(N, T1, Lq, Lv, 2, generator=g).cuda()
     go = torch.randn(N, T1, Lq, M * D, generator=g).cuda()
+    dt = 2 if bf16 else 0
+    if bf16:
+        value, go = value.bfloat16(), go.bfloat16()
     out = torch.empty_like(go)
-    gv, goff, glog = torch.empty_like(value), torch.empty_like(offsets), torch.empty_like(logits)
+    gv, goff, glog = torch.empty(value.shape, device="cuda"), torch.empty_like(offsets), torch.empty_like(logits)
     shapes, lsi = shapes.cuda(), lsi.cuda()
     st = torch.cuda.current_stream().cuda_stream
     keep = (value, offsets, logits, ref, go, out, gv, goff, glog, shapes, lsi)
@@ -184,21 +194,21 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
     def fwd():
         r = L.msda_snippet_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                    logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
-                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, st)
+                                   Lv, Lq, P, 0, 0, rs[0], rs[1], dt, st)
         assert r == 0, r
 
     def bwd():
         r = L.msda_snippet_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], 0, 0, st)
+                                    0, 0, rs[0], rs[1], dt, 0, st)
         assert r == 0, r
 
-    e = 4
+    e = 2 if bf16 else 4   # value / output / grad_output element size; everything else is fp32
     samples = N * T1 * Lq * M * Lv * P
     vbytes = min(N * T2 * S * M * D, 4 * samples * D * 3)
-    fwd_b = e * (vbytes + 3 * samples + N * T1 * Lq * M * D)
-    bwd_b = e * (2 * vbytes + N * T1 * Lq * M * D + 6 * samples)
+    fwd_b = e * (vbytes + N * T1 * Lq * M * D) + 4 * 3 * samples
+    bwd_b = e * (vbytes + N * T1 * Lq * M * D) + 4 * (vbytes + 6 * samples)
     return fwd, bwd, fwd_b, bwd_b, keep
 
 
@@ -211,6 +221,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="tile length knob for D=48 (8/16/32)")
     ap.add_argument("--snip-pairs", type=int, default=0)
     ap.add_argument("--fwd-variant", type=int, default=-1, help="msda_set_tuning('fwd_variant') experiment switch")
+    ap.add_argument("--bf16", action="store_true", help="also time the bf16 I/O mode")
     ap.add_argument("--head-major", action="store_true",
                     help="also time the per-call kernels on a head-major copy (value (N*M,S,1,D)): what a packed value layout would give")
     ap.add_argument("--warmup", type=int, default=5)
@@ -238,9 +249,13 @@ def main():
         if name not in args.cases.split(","):
             continue
         fwd, bwd, fb, bb, keep = snippet_calls(N, T1, 4, Lq, encoder=enc, regime=args.regime)
-        for which, fn, nbytes in (("fwd", fwd, fb), ("bwd", bwd, bb)):
+        rows = [("ours_fused_layer", "fwd", fwd, fb), ("ours_fused_layer", "bwd", bwd, bb)]
+        if args.bf16:
+            hf, hb, hfb, hbb, hkeep = snippet_calls(N, T1, 4, Lq, encoder=enc, regime=args.regime, bf16=True)
+            rows += [("ours_fused_layer_bf16", "fwd", hf, hfb), ("ours_fused_layer_bf16", "bwd", hb, hbb)]
+        for impl, which, fn, nbytes in rows:
             med, best = time_fn(fn, args.iters, args.flush)
-            print(json.dumps({"case": name, "impl": "ours_fused_layer", "pass": which, "us_median": round(med, 2),
+            print(json.dumps({"case": name, "impl": impl, "pass": which, "us_median": round(med, 2),
                               "us_best": round(best, 2), "alg_MB": round(nbytes / 1e6, 2),
                               "GBps": round(nbytes / med / 1e3, 1),
                               "frac_of_measured_hbm": round(nbytes / med / 1e3 / PEAK, 4),
@@ -257,6 +272,12 @@ def main():
         if ref is not None:
             rows += [("vendored", "fwd", lambda: ref.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 64), fb),
                      ("vendored", "bwd", lambda: ref.ms_deform_attn_backward(value, shapes, lsi, loc, attn, go, 64), bb)]
+        if args.bf16:
+            v16 = min(N * S * 8 * 48, 4 * N * Lq * 8 * 3 * 4 * 48)
+            fb16 = 2 * (v16 + N * Lq * 8 * 48) + 4 * 3 * N * Lq * 8 * 12
+            bb16 = 2 * (v16 + N * Lq * 8 * 48) + 4 * (v16 + 6 * N * Lq * 8 * 12)
+            bfwd, bbwd, _, _, bkeep = direct_calls(value, shapes, lsi, loc, attn, go, bf16=True)
+            rows += [("ours_bf16", "fwd", bfwd, fb16), ("ours_bf16", "bwd", bbwd, bb16)]
         if args.head_major:
             N_, S_, M_, D_ = value.shape
             hv = value.permute(0, 2, 1, 3).reshape(N_ * M_, S_, 1, D_).contiguous()
