@@ -410,6 +410,12 @@ cudaError_t launch_snippet_forward_bf16(const void *value_, const int64_t *shape
 {
     const __nv_bfloat16 *value = static_cast<const __nv_bfloat16 *>(value_);
     __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(out_);
+    // few CTAs (decoder layers): latency-bound -- 8-byte lanes give twice the threads per query
+    if ((long long)((d.Lq + 15) / 16) * d.M * d.N * d.T1 < 148 * 3) {
+#define CALL(VT, LN, PR) launch_snip_fwd<bf16q, LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
+        MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+    }
 #define CALL(VT, LN, PR) launch_snip_fwd<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
     MSDA_DISPATCH_LANES_BF16(d.D, CALL)
 #undef CALL
