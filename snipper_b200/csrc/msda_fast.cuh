@@ -417,6 +417,6 @@ __device__ __forceinline__ void subgroup_sum3(float &a, float &b, float &c)
 }
 
 // lanes per shuffle sub-group for a pair of LANES lanes (pairs never straddle a sub-group)
-constexpr int sub_group(int lanes) { return lanes % 4 == 0 ? 4 : 2; }
+__host__ __device__ constexpr int sub_group(int lanes) { return lanes % 4 == 0 ? 4 : 2; }
 
 }  // namespace msda

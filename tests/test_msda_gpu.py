@@ -357,3 +357,4 @@ def test_pile_up_on_one_cell_long_list_path():
                             c["grad_out"].double())
     for got, want in zip(a, ref):
         assert rel_err(got, want) < BWD_TOL
+
