@@ -392,6 +392,26 @@ __device__ __forceinline__ void gather_scatter(const SampleMeta mt, const BwdWei
     py = fmaf(b.hx, d2 - d0, fmaf(b.lx, d3 - d1, py));
 }
 
+// Which 16-byte chunk of the head slice a lane owns.  For fp32 D = 48 a 192-byte slice starts at byte
+// 0 or 64 of a 128-byte line and spans two lines; a query whose 12 lanes straddle a warp boundary
+// (8|4 or 4|8) would make one of the two warps touch BOTH lines.  Rotating the chunk assignment of
+// those queries puts whole lines on each side of the boundary: 2.0 instead of 2.12 L1 wavefronts
+// per gathered slice (and per vector reduction).  Results do not depend on it.
+template <typename VT, int LANES>
+__device__ __forceinline__ int lane_chunk(int tid, int lane, int m)
+{
+    if (LANES == 12 && sizeof(typename Chunk<VT>::elem) == 4 && Chunk<VT>::BYTES == 16) {
+        const int k = 32 - ((tid - lane) & 31);     // lanes of this query before the next warp boundary
+        if (k < 12) {                                // k is 4 or 8
+            const bool odd = ((m * LANES * 16) & 127) != 0;  // slice starts mid-line
+            const int rot = odd ? (k == 8 ? 4 : 0) : (k == 8 ? 0 : 8);
+            const int c = lane + rot;
+            return c >= 12 ? c - 12 : c;
+        }
+    }
+    return lane;
+}
+
 // Queries per CTA tile for D = 48.  The tuned default is 16; when that would leave the GPU with
 // fewer than ~3 CTAs per SM (decoder: Lq = 60) halve the tile so twice as many CTAs are in flight
 // -- those launches are latency-bound, not bandwidth-bound.

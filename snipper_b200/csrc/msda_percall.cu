@@ -77,9 +77,10 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
     const bool live = q0 + pl < a.Lq;
+    const int chunk = lane_chunk<VT, LANES>(tid, lane, m);
     const size_t pair = ((size_t)nb * a.Lq + q0 + pl) * a.M + m;
     const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
-                     (size_t)(m * LANES + lane) * C::BYTES;
+                     (size_t)(m * LANES + chunk) * C::BYTES;
     C acc = zero_chunk<C>();
 
     for (int lp0 = 0; lp0 < LP; lp0 += a.cl) {
@@ -122,7 +123,7 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
         }
         if (lp0 + a.cl < LP) __syncthreads();  // staging buffers are reused by the next pass
     }
-    if (live) acc.store(reinterpret_cast<char *>(out) + (pair * LANES + lane) * C::BYTES);
+    if (live) acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
 }
 
 // SCATTER == false: grad_sampling_loc / grad_attn_weight only (deterministic mode computes
@@ -156,14 +157,15 @@ msda_bwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
     const int sub = lane / Cfg::SUBG;
+    const int chunk = lane_chunk<VT, LANES>(tid, lane, m);
     const bool live = q0 + pl < a.Lq;
     const size_t pair = ((size_t)nb * a.Lq + q0 + pl) * a.M + m;
     const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
-                     (size_t)(m * LANES + lane) * C::BYTES;
+                     (size_t)(m * LANES + chunk) * C::BYTES;
     char *gp0 = reinterpret_cast<char *>(grad_value) + ((size_t)nb * a.S * a.cell_bytes + (size_t)m * LANES * C::BYTES) * GS +
-                RedView<VT>::lane_offset(lane);
+                RedView<VT>::lane_offset(chunk);
     C g = zero_chunk<C>();
-    if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + lane) * C::BYTES);
+    if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + chunk) * C::BYTES);
     const RedView<VT> gr = RedView<VT>::make(g);
 
     for (int lp0 = 0; lp0 < LP; lp0 += a.cl) {

@@ -52,9 +52,14 @@ __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo
 // Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each query is
 // done cooperatively through shared memory (one expf per sample), then
 // loc = ref + offset / (W_l, H_l) in the reference's operation order (ms_deform_attn.py:164-165).
-// FWD: second = per-corner weights (bilinear x A).  BWD: second = {lx, ly, A, -}.   A = softmax / k.
-template <int THREADS, int PAIRS, bool FWD>
-__device__ __forceinline__ void snippet_phase1(SampleMeta *meta, float4 *second, float *zs, float *es,
+// Each sample is parked as ONE 16-byte record {lx, ly, A, off | mask}: A = softmax / k, `off` the
+// byte offset of the (y0,x0) cell (a multiple of 16, so its low four bits carry the corner mask).
+// One LDS.128 per sample and lane in phase 2 instead of an LDS.64 + an LDS.128 -- wide shared loads
+// cost one L1 wavefront per quarter warp, and the L1 data pipe is what bounds these kernels
+// (profiles/r01_run18_*); the row stride comes from the level table once per level, and the four
+// corner weights are recomputed per lane (8 FP instructions, the issue slots are free).
+template <int THREADS, int PAIRS>
+__device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es,
                                                const LevelTable &lv, const SnipArgs &a, int n, int t1, int q0,
                                                int m, size_t qbase, const float *__restrict__ offsets,
                                                const float *__restrict__ logits,
@@ -80,8 +85,7 @@ __device__ __forceinline__ void snippet_phase1(SampleMeta *meta, float4 *second,
         const int spl = fast_div(i, a.magic_LP);
         const int lp = i - spl * LP;
         const int q = q0 + spl;
-        SampleMeta mt = empty_meta();
-        float4 sec = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 r = make_float4(0.f, 0.f, 0.f, __int_as_float(0));  // mask 0: inactive
         if (q < d.Lq) {
             const float *e = es + spl * LP;
             float sum = 0.f;
@@ -94,18 +98,21 @@ __device__ __forceinline__ void snippet_phase1(SampleMeta *meta, float4 *second,
             const float u = __ldg(rp) + o.x / (float)lv.W[l];
             const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
             const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
-            mt = make_meta(s, lv.W[l], a.cell_bytes);
-            if (FWD) {
-                const float hx = 1.f - s.lx, hy = 1.f - s.ly;
-                sec = make_float4(hy * hx * at, hy * s.lx * at, s.ly * hx * at, s.ly * s.lx * at);
-            } else {
-                sec = make_float4(s.lx, s.ly, at, 0.f);
-            }
+            r = make_float4(s.lx, s.ly, at, __int_as_float((s.base * a.cell_bytes) | s.mask));
         }
-        meta[i] = mt;
-        second[i + spl] = sec;  // 16-byte records strided LP + 1 per query (bank-conflict-free LDS.128)
+        rec[i + spl] = r;  // records strided LP + 1 per query
     }
     __syncthreads();
+}
+
+// Unpack a record into the SampleMeta the gather helpers take (row = W_l * cell_bytes).
+__device__ __forceinline__ SampleMeta record_meta(const float4 &r, unsigned row)
+{
+    const int om = __float_as_int(r.w);
+    SampleMeta mt;
+    mt.off = om & ~15;
+    mt.wm = row | ((unsigned)(om & 15) << 28);
+    return mt;
 }
 
 template <typename VT, int LANES, int PAIRS, int CSB>
@@ -122,10 +129,8 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
-    float4 *wts = reinterpret_cast<float4 *>(smem_raw);
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
-    float *zs = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1) +
-                                          sizeof(SampleMeta) * Cfg::PAIRS * LP);
+    float4 *rec = reinterpret_cast<float4 *>(smem_raw);
+    float *zs = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
     float *es = zs + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
@@ -138,22 +143,31 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
-    snippet_phase1<Cfg::THREADS, Cfg::PAIRS, true>(meta, wts, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits,
-                                                  ref, 1.f / (float)nf);
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits, ref,
+                                            1.f / (float)nf);
 
     // ---- phase 2: gather from every neighbour frame ----
     const int pl = tid / LANES;
     const int lane = tid - pl * LANES;
     if (q0 + pl >= d.Lq) return;
+    const int chunk = lane_chunk<VT, LANES>(tid, lane, m);
     const size_t pair = (qbase + q0 + pl) * d.M + m;
     const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
-                     (size_t)(m * LANES + lane) * C::BYTES;
+                     (size_t)(m * LANES + chunk) * C::BYTES;
     const int64_t fstride = d.value_stride_t * (int64_t)sizeof(ET);  // bytes between frames
-    const SampleMeta *mm = meta + pl * LP;
-    const float4 *ww = wts + pl * (LP + 1);
+    const float4 *rr = rec + pl * (LP + 1);
     C acc = zero_chunk<C>();
-    for (int j = 0; j < LP; ++j) gather_fma_frames<VT, CSB>(acc, mm[j], ww[j], pf, fstride, nf, a.cell_bytes);
-    acc.store(reinterpret_cast<char *>(out) + (pair * LANES + lane) * C::BYTES);
+    for (int l = 0; l < d.L; ++l) {
+        const unsigned row = (unsigned)(lv.W[l] * a.cell_bytes);
+        for (int p = 0; p < d.P; ++p) {
+            const float4 r = rr[l * d.P + p];
+            const float hx = 1.f - r.x, hy = 1.f - r.y;
+            const float ah = hy * r.z, al = r.y * r.z;
+            const float4 w = make_float4(ah * hx, ah * r.x, al * hx, al * r.x);
+            gather_fma_frames<VT, CSB>(acc, record_meta(r, row), w, pf, fstride, nf, a.cell_bytes);
+        }
+    }
+    acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
 }
 
 template <typename VT, int LANES, int PAIRS, int CSB>
@@ -173,10 +187,8 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
-    float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1) +
-                                            sizeof(SampleMeta) * Cfg::PAIRS * LP);
+    float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, off | mask}
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
     float *zs = part;  // phase-1 scratch aliases `part` ([rec][SUBS][3] >= 2 floats per record)
     float *es = part + Cfg::PAIRS * LP;
 
@@ -190,33 +202,33 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
 
     load_level_table(lv, shapes, lsi, d.L);
     __syncthreads();
-    snippet_phase1<Cfg::THREADS, Cfg::PAIRS, false>(meta, frac, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits,
-                                                   ref, 1.f / (float)nf);
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(frac, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits, ref,
+                                            1.f / (float)nf);
 
     // ---- phase 2: every thread participates (full-mask shuffles) ----
     {
         const int pl = tid / LANES;
         const int lane = tid - pl * LANES;
         const int sub = lane / Cfg::SUBG;
+        const int chunk = lane_chunk<VT, LANES>(tid, lane, m);
         const bool live = q0 + pl < d.Lq;
         const size_t pair = (qbase + q0 + pl) * d.M + m;
         const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
-                         (size_t)(m * LANES + lane) * C::BYTES;
+                         (size_t)(m * LANES + chunk) * C::BYTES;
         // grad_value is a dense fp32 (N,T2,S,M,D) buffer: GS x the value byte offsets
         char *gpf = reinterpret_cast<char *>(grad_value) +
                     (((size_t)n * d.T2 + lo) * d.S * a.cell_bytes + (size_t)m * LANES * C::BYTES) * GS +
-                    RedView<VT>::lane_offset(lane);
+                    RedView<VT>::lane_offset(chunk);
         C g = zero_chunk<C>();
-        if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + lane) * C::BYTES);
+        if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + chunk) * C::BYTES);
         const RedView<VT> gr = RedView<VT>::make(g);
         const int64_t fstride = d.value_stride_t * (int64_t)sizeof(ET);
         const int64_t gfstride = (int64_t)d.S * a.cell_bytes * GS;
-        const SampleMeta *mm = meta + pl * LP;
         const float4 *ff = frac + pl * (LP + 1);
         float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
         for (int j = 0; j < LP; ++j) {
-            const SampleMeta mt = mm[j];
             const float4 f = ff[j];
+            const SampleMeta mt = record_meta(f, (unsigned)(lv.W[fast_div(j, a.magic_P)] * a.cell_bytes));
             const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
             float pa = 0.f, px = 0.f, py = 0.f;
             const char *p0 = pf;
@@ -307,8 +319,7 @@ static cudaError_t launch_snip_fwd(const typename Chunk<VT>::elem *value, const 
     using Cfg = SnipCfg<LANES, PAIRS>;
     const SnipArgs a = make_snip_args<VT>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) +
-                        (sizeof(SampleMeta) + 2 * sizeof(float)) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + 2 * sizeof(float) * Cfg::PAIRS * d.L * d.P;
     constexpr int C = snip_csb<VT, LANES>();
     if (C != 0 && d.M * d.D == 384)
         msda_snippet_fwd_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(
@@ -328,8 +339,7 @@ static cudaError_t launch_snip_bwd_impl(const typename Chunk<VT>::elem *value, c
     using Cfg = SnipCfg<LANES, PAIRS>;
     const SnipArgs a = make_snip_args<VT>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) +
-                        (sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + sizeof(float) * 3 * Cfg::SUBS * Cfg::PAIRS * d.L * d.P;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB><<<grid, Cfg::THREADS, smem, stream>>>(
