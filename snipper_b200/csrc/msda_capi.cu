@@ -8,7 +8,6 @@
 
 namespace msda {
 extern int g_pairs_d48;
-extern int g_fwd_variant;
 extern int g_snip_pairs_d48;
 }  // namespace msda
 
@@ -58,7 +57,6 @@ int msda_last_cuda_error(void) { return g_last_cuda_error; }
 int msda_set_tuning(const char *key, int value)
 {
     if (key == nullptr) return MSDA_ERR_INVALID_ARGUMENT;
-    if (!strcmp(key, "fwd_variant") && value >= 0 && value <= 2) { msda::g_fwd_variant = value; return MSDA_OK; }
     const bool ok = (value == 8 || value == 16 || value == 32);
     if (!strcmp(key, "pairs_d48") && ok) { msda::g_pairs_d48 = value; return MSDA_OK; }
     if (!strcmp(key, "snip_pairs_d48") && ok) { msda::g_snip_pairs_d48 = value; return MSDA_OK; }

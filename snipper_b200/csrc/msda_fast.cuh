@@ -258,35 +258,6 @@ __device__ __forceinline__ void gather_fma(Chunk<VT> &acc, const SampleMeta mt, 
     }
 }
 
-// Two samples per step: when both have all four corners, the eight gathers are issued before any
-// of the FFMAs so twice as many loads are in flight per warp.
-template <typename VT, int CSB>
-__device__ __forceinline__ void gather_fma2(Chunk<VT> &acc, const SampleMeta m0, const float4 w0, const SampleMeta m1,
-                                            const float4 w1, const char *__restrict__ p0, int runtime_csb)
-{
-    using C = Chunk<VT>;
-    const int csb = cell_stride_bytes<CSB>(runtime_csb);
-    if (m0.wm >= kAllCorners && m1.wm >= kAllCorners) {
-        const char *a0 = p0 + (ptrdiff_t)m0.off;
-        const char *a2 = a0 + (m0.wm & 0x0fffffffu);
-        const char *b0 = p0 + (ptrdiff_t)m1.off;
-        const char *b2 = b0 + (m1.wm & 0x0fffffffu);
-        const C v0 = C::load(a0);
-        const C v1 = C::load(a0 + csb);
-        const C v2 = C::load(a2);
-        const C v3 = C::load(a2 + csb);
-        const C u0 = C::load(b0);
-        const C u1 = C::load(b0 + csb);
-        const C u2 = C::load(b2);
-        const C u3 = C::load(b2 + csb);
-        fma_chunk(acc, w0.x, v0); fma_chunk(acc, w0.y, v1); fma_chunk(acc, w0.z, v2); fma_chunk(acc, w0.w, v3);
-        fma_chunk(acc, w1.x, u0); fma_chunk(acc, w1.y, u1); fma_chunk(acc, w1.z, u2); fma_chunk(acc, w1.w, u3);
-    } else {
-        gather_fma<VT, CSB>(acc, m0, w0, p0, runtime_csb);
-        gather_fma<VT, CSB>(acc, m1, w1, p0, runtime_csb);
-    }
-}
-
 // Same, over `nf` consecutive value frames (fused snippet kernel): the sample set-up is shared by all
 // neighbour frames, so the fast/slow decision is taken once and the frame loop is branch-free,
 // which lets the loads of two frames overlap.

@@ -39,8 +39,6 @@ struct FastCfg {
     static_assert(LANES % 2 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
-int g_fwd_variant = 1;  // msda_set_tuning("fwd_variant", 0|1|2): 1 (two samples per step) measured best, profiles/r01_run9_*
-
 struct FastArgs {
     int M, L, P, Lq, S;
     int cell_bytes;            // M * D * sizeof(VT): bytes between consecutive cells of `value`
@@ -49,12 +47,12 @@ struct FastArgs {
     int64_t value_batch_stride;  // elements
 };
 
-// VAR (msda_set_tuning("fwd_variant")): 0 = one sample per step; 1 = two samples per step
-// (gather_fma2, default); 2 = as 0 with the register cap that admits 10 CTAs per SM.
-template <typename VT, int LANES, int PAIRS, int CSB, int VAR = 0>
-__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS,
-                                  VAR == 2 ? 1920 / FastCfg<LANES, PAIRS>::THREADS
-                                           : (VAR == 1 ? 960 / FastCfg<LANES, PAIRS>::THREADS : 0))
+// No occupancy floor in the launch bounds: left alone ptxas needs 40 registers (8 CTAs of 192 threads per
+// SM).  Variants that trade occupancy for loads in flight (two samples per step at 64 registers, a
+// 32-register build) measured equal or slower once the chunk rotation was in (profiles/r01_run9_*,
+// r01_run22_*).
+template <typename VT, int LANES, int PAIRS, int CSB>
+__global__ void __launch_bounds__(FastCfg<LANES, PAIRS>::THREADS)
 msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                      const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                      const float *__restrict__ attn, typename Chunk<VT>::elem *__restrict__ out, const FastArgs a)
@@ -110,16 +108,8 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
         if (live) {
             const SampleMeta *mm = meta + pl * n;
             const float4 *ww = wts + pl * (n + 1);
-            if (VAR == 1) {
-                int j = 0;
-#pragma unroll 2
-                for (; j + 1 < n; j += 2)
-                    gather_fma2<VT, CSB>(acc, mm[j], ww[j], mm[j + 1], ww[j + 1], p0, a.cell_bytes);
-                if (j < n) gather_fma<VT, CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
-            } else {
 #pragma unroll 4
-                for (int j = 0; j < n; ++j) gather_fma<VT, CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
-            }
+            for (int j = 0; j < n; ++j) gather_fma<VT, CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
         }
         if (lp0 + a.cl < LP) __syncthreads();  // staging buffers are reused by the next pass
     }
@@ -281,14 +271,9 @@ static cudaError_t launch_fwd_fast(const typename Chunk<VT>::elem *value, const 
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) + sizeof(SampleMeta) * Cfg::PAIRS * a.cl;
     constexpr int C = snipper_csb<VT, LANES>();
-    if (C != 0 && d.M * d.D == 384) {
-        if (g_fwd_variant == 1)
-            msda_fwd_fast_kernel<VT, LANES, PAIRS, C, (C != 0 ? 1 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
-        else if (g_fwd_variant == 2)
-            msda_fwd_fast_kernel<VT, LANES, PAIRS, C, (C != 0 ? 2 : 0)><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
-        else
-            msda_fwd_fast_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
-    } else
+    if (C != 0 && d.M * d.D == 384)
+        msda_fwd_fast_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+    else
         msda_fwd_fast_kernel<VT, LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
     return cudaGetLastError();
 }

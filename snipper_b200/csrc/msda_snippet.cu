@@ -30,8 +30,7 @@ struct SnipCfg {
     static constexpr int THREADS = PAIRS * LANES;
     static constexpr int SUBG = sub_group(LANES);
     static constexpr int SUBS = LANES / SUBG;
-    // register caps: >= 1152 resident threads/SM forward (<= 56 regs), >= 768 backward (<= 80 regs)
-    static constexpr int FWD_MIN_BLOCKS = 1152 / THREADS < 1 ? 1 : (1152 / THREADS > 16 ? 16 : 1152 / THREADS);
+    // register cap of the backward: >= 768 resident threads/SM (<= 80 regs)
     static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : (768 / THREADS > 16 ? 16 : 768 / THREADS);
     static_assert(LANES % 2 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
@@ -115,8 +114,12 @@ __device__ __forceinline__ SampleMeta record_meta(const float4 &r, unsigned row)
     return mt;
 }
 
+// No occupancy floor in the launch bounds on purpose: given a register budget ptxas hoists loads
+// until it is used up (56 registers + spills at a 6-CTA floor, 64 at 5, 80 at 4) and the kernel gets
+// SLOWER -- left alone it needs 40 registers, 8 CTAs per SM fit, and the gather is 10-13 % faster
+// (profiles/r01_run21_*): this kernel wants warps in flight, not loads per warp.
 template <typename VT, int LANES, int PAIRS, int CSB>
-__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::FWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS)
 msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,

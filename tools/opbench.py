@@ -220,7 +220,6 @@ def main():
     ap.add_argument("--regime", default="local")
     ap.add_argument("--pairs", type=int, default=0, help="tile length knob for D=48 (8/16/32)")
     ap.add_argument("--snip-pairs", type=int, default=0)
-    ap.add_argument("--fwd-variant", type=int, default=-1, help="msda_set_tuning('fwd_variant') experiment switch")
     ap.add_argument("--bf16", action="store_true", help="also time the bf16 I/O mode")
     ap.add_argument("--head-major", action="store_true",
                     help="also time the per-call kernels on a head-major copy (value (N*M,S,1,D)): what a packed value layout would give")
@@ -235,8 +234,6 @@ def main():
     from snipper_b200 import capi
     if args.pairs:
         assert capi.lib().msda_set_tuning(b"pairs_d48", args.pairs) == 0
-    if args.fwd_variant >= 0:
-        assert capi.lib().msda_set_tuning(b"fwd_variant", args.fwd_variant) == 0
     ref = None
     if args.ref:
         from oracle.build_ref import load_ref
@@ -291,8 +288,7 @@ def main():
             print(json.dumps({"case": name, "impl": impl, "pass": which, "us_median": round(med, 2),
                               "us_best": round(best, 2), "alg_MB": round(nbytes / 1e6, 2),
                               "GBps": round(nbytes / med / 1e3, 1), "frac_of_measured_hbm": round(nbytes / med / 1e3 / PEAK, 4),
-                              "l2_flush": args.flush, "regime": args.regime, "pairs": args.pairs or 16,
-                              "fwd_variant": args.fwd_variant}))
+                              "l2_flush": args.flush, "regime": args.regime, "pairs": args.pairs or 16}))
 
 
 if __name__ == "__main__":
