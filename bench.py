@@ -104,7 +104,7 @@ def fused_layer_bytes(dims, e=4):
     N, T2, T1, S, M, D, L, Lq, P = dims
     samples = N * T1 * Lq * M * L * P
     value = min(N * T2 * S * M * D, 4 * samples * D * 3)
-    return e * (value + 3 * samples + N * T1 * Lq * M * D)
+    return e * (value + N * T1 * Lq * M * D) + 4 * 3 * samples  # offsets / logits are fp32 in every mode
 
 
 # ------------------------------------------------------------------------------------------
@@ -161,6 +161,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"],
+                    help="NOT the headline: 'tf32' lets cuBLAS use TF32 tensor cores for the stock Linear layers, "
+                         "'bf16' runs the network under torch.autocast(bfloat16) (bf16 GEMMs, bf16 MSDA gathers). "
+                         "The default and the number the driver records is fp32.")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -184,6 +188,10 @@ def main():
     from snipper_b200.harness.snipper_net import build_snipper
 
     args.warmup = max(args.warmup, 3)
+    if args.precision == "tf32":
+        torch.backends.cuda.matmul.allow_tf32 = True
+    import contextlib
+    autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if args.precision == "bf16" else contextlib.nullcontext
     torch.manual_seed(42)  # reference main.py:48
     model = build_snipper(snipper_b200.MSDeformAttn).to(dev).eval()
     host = [x.pin_memory() for x in synthetic_snippets(N_INPUTS, seed=1000 + rank)]  # every rank its own shard
@@ -205,10 +213,10 @@ def main():
     # ---- build the step functions -------------------------------------------------------
     use_graph = not args.no_graph
     static_in = torch.empty_like(resident[0])
-    with torch.no_grad():
+    with torch.no_grad(), autocast():
         for i in range(2):  # lazy init (cuDNN autotune, cuBLAS handles) before capture
             out, _ = model(resident[i])
-            result = pack_result(out)
+            result = pack_result(out).float()
     d2h_bytes = result.numel() * result.element_size()
     host_out = torch.empty(result.shape, dtype=result.dtype).pin_memory()
     graph, launches_per_step = None, None
@@ -217,9 +225,9 @@ def main():
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(graph):
+            with torch.no_grad(), autocast(), torch.cuda.graph(graph):
                 out, _ = model(static_in)
-                static_result = pack_result(out)
+                static_result = pack_result(out).float()
             launches_per_step = ops.STATS.launches
         except Exception as e:  # fall back to eager timing, say so in config
             print("[bench] CUDA graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
@@ -227,16 +235,16 @@ def main():
             torch.cuda.synchronize()
 
     def step_resident(i):
-        with torch.no_grad():
+        with torch.no_grad(), autocast():
             if graph is not None:
                 static_in.copy_(resident[i % N_INPUTS])  # device->device, keeps inputs rotating
                 graph.replay()
                 return static_result
             out, _ = model(resident[i % N_INPUTS])
-            return pack_result(out)
+            return pack_result(out).float()
 
     def step_e2e(i):
-        with torch.no_grad():
+        with torch.no_grad(), autocast():
             if graph is not None:
                 static_in.copy_(host[i % N_INPUTS], non_blocking=True)
                 graph.replay()
@@ -244,7 +252,7 @@ def main():
             else:
                 x = host[i % N_INPUTS].to(dev, non_blocking=True)
                 out, _ = model(x)
-                host_out.copy_(pack_result(out), non_blocking=True)
+                host_out.copy_(pack_result(out).float(), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
         return host_out
 
@@ -275,7 +283,7 @@ def main():
     # ---- roofline of the dominant kernel: events around every fused-layer launch, eager steps ----
     ops.STATS.reset()
     ops.STATS.timing = True
-    with torch.no_grad():
+    with torch.no_grad(), autocast():
         for i in range(args.steps):
             model(resident[i % N_INPUTS])
     torch.cuda.synchronize()
@@ -285,7 +293,7 @@ def main():
     dom_avg_ms = sum(dom_ms) / len(dom_ms)
     msda_ms_per_step = sum(sum(v) for v in per_kernel.values()) / args.steps
     peak, peak_src = measured_peak()
-    alg_bytes = fused_layer_bytes(dom_dims)
+    alg_bytes = fused_layer_bytes(dom_dims, e=2 if args.precision == "bf16" else 4)
     achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -305,7 +313,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32-matmul (informational)", "bf16": "bf16-autocast (informational)"}[args.precision],
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "snippets_per_gpu_per_step": 1, "parallelism": "snippet-sharded x%d, no collective" % world,
                    "launch": "cuda_graph_replay" if graph is not None else "eager",
                    "l2": "working set per step (171 MB weights + >1 GB activations) exceeds the 126 MB L2; %d distinct inputs rotated" % N_INPUTS,
