@@ -30,8 +30,7 @@ struct SnipCfg {
     static constexpr int THREADS = PAIRS * LANES;
     static constexpr int SUBG = sub_group(LANES);
     static constexpr int SUBS = LANES / SUBG;
-    // register cap of the backward: >= 768 resident threads/SM (<= 80 regs)
-    static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : (768 / THREADS > 16 ? 16 : 768 / THREADS);
+    static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : (768 / THREADS > 16 ? 16 : 768 / THREADS);  // <= 80 regs
     static_assert(LANES % 2 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
@@ -236,6 +235,8 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
             float pa = 0.f, px = 0.f, py = 0.f;
             const char *p0 = pf;
             char *gp0 = gpf;
+            // (the backward, unlike the forward, prefers loads in flight over occupancy: not unrolling
+            //  this loop -- 64 registers, 5 CTAs per SM -- measured 4-7 % slower, profiles/r01_run24_*)
             for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
                 gather_scatter<VT, CSB, true>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
             subgroup_sum3<Cfg::SUBG>(pa, px, py);
@@ -250,14 +251,11 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
 
     // ---- phase 3: per-sample finish + softmax backward ----
     // dL/dz_i = A_i * (gA_i - k * sum_j gA_j A_j)   with A = softmax/k, gA_i = <G, val_i> summed over frames
-    float pa_i[(Cfg::PAIRS * kSnippetMaxLP + Cfg::THREADS - 1) / Cfg::THREADS];
-    int it = 0;
-    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS, ++it) {
+    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
         const float *p = part + (size_t)i * (Cfg::SUBS * 3);
         float pa = 0.f, px = 0.f, py = 0.f;
 #pragma unroll
         for (int s = 0; s < Cfg::SUBS; ++s) { pa += p[3 * s]; px += p[3 * s + 1]; py += p[3 * s + 2]; }
-        pa_i[it] = pa;
         const int spl = fast_div(i, a.magic_LP);
         const float at = frac[i + spl].z;
         if (q0 + spl < d.Lq) {
@@ -266,17 +264,17 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
             const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
             reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(at * px, at * py);
         }
-        part[(size_t)i * (Cfg::SUBS * 3)] = pa * at;  // own slot only
+        part[(size_t)i * (Cfg::SUBS * 3)] = pa * at;  // own slots only ([0] = gA_i A_i, [1] = gA_i)
+        part[(size_t)i * (Cfg::SUBS * 3) + 1] = pa;
     }
     __syncthreads();
-    it = 0;
-    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS, ++it) {
+    for (int i = tid; i < Cfg::PAIRS * LP; i += Cfg::THREADS) {
         const int spl = fast_div(i, a.magic_LP);
         if (q0 + spl < d.Lq) {
             float dot = 0.f;
             for (int j = 0; j < LP; ++j) dot += part[(size_t)(spl * LP + j) * (Cfg::SUBS * 3)];
             const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
-            grad_logits[si] = frac[i + spl].z * (pa_i[it] - (float)nf * dot);
+            grad_logits[si] = frac[i + spl].z * (part[(size_t)i * (Cfg::SUBS * 3) + 1] - (float)nf * dot);
         }
     }
 }
