@@ -98,6 +98,24 @@ def pack_result(out):
     return torch.cat([out["pred_logits"].flatten(), out["pred_kpts2d"].flatten(), out["pred_depth"].flatten()])
 
 
+def fused_layer_gathered_bytes(dims, n_frame, e=4):
+    """Bytes the fused layer kernel gathers through L1: 4 corners x D channels per sample and neighbour
+    frame (reference ms_deform_attn.py:137-140: frames t1-1, t1, t1+1 clipped; all frames for future t1)."""
+    N, T2, T1, S, M, D, L, Lq, P = dims
+    pairs = sum(len([t for t in (t1 - 1, t1, t1 + 1) if 0 <= t < n_frame]) if t1 < n_frame else T2 for t1 in range(T1))
+    return N * pairs * Lq * M * L * P * 4 * D * e
+
+
+def measured_l1_gather_ceiling():
+    """TB/s of 192-byte-slice gathers the L1 data pipe sustains on this GPU model (tools/micro/l1_tex_vs_ldg.cu,
+    profiles/r01_run25_*): the on-chip ceiling of any one-load-per-corner formulation."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_run25_micro_l1_gather_ceiling_ldg_vs_tex.jsonl")) as f:
+            return max(json.loads(line)["ldg_TBps"] for line in f if line.strip())
+    except Exception:
+        return None
+
+
 def fused_layer_bytes(dims, e=4):
     """Algorithmic bytes of one fused layer launch (fused-snippet accounting):
     value read once, offsets(2)+logits(1) once per sample, output once."""
@@ -295,6 +313,15 @@ def main():
     peak, peak_src = measured_peak()
     alg_bytes = fused_layer_bytes(dom_dims, e=2 if args.precision == "bf16" else 4)
     achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
+    e_bytes = 2 if args.precision == "bf16" else 4
+    gathered = fused_layer_gathered_bytes(dom_dims, model.num_frames, e_bytes)
+    ceiling = measured_l1_gather_ceiling()
+    on_chip = {"what": "bytes gathered through L1 per launch (4 corners x D channels per sample and neighbour frame) / launch time, "
+                       "against the measured L1 gather ceiling for 192-byte slices (tools/micro/l1_tex_vs_ldg.cu): the resource "
+                       "that actually bounds this kernel (ncu: l1tex data-pipe wavefronts 85-88 % of peak, DRAM 7 %)",
+               "gathered_bytes_per_launch": gathered, "achieved_TBps": gathered / (dom_avg_ms * 1e-3) / 1e12,
+               "measured_ceiling_TBps": ceiling,
+               "frac": (gathered / (dom_avg_ms * 1e-3) / 1e12 / ceiling) if ceiling else None}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
@@ -328,7 +355,8 @@ def main():
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": dom_avg_ms, "launches_timed": len(dom_ms),
-                     "how": "CUDA events on the launching stream around each launch, eager steps after the timed region"},
+                     "how": "CUDA events on the launching stream around each launch, eager steps after the timed region",
+                     "on_chip": on_chip},
     }
     if world == 1 and not args.no_cpu_baseline:
         times, cores = cpu_reference_run(1, 0)

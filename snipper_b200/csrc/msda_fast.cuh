@@ -5,20 +5,20 @@
 // slices and every gathered cell is consumed as full 32-byte sectors.
 //
 //   phase 1  one thread per SAMPLE (query, level, point): bilinear set-up done once and parked
-//            in shared memory as
-//                SampleMeta {byte offset of the (y0,x0) cell, row stride | corner mask}  (8 B)
-//                float4     per-corner weights (forward) or {lx, ly, A, -} (backward)   (16 B)
+//            in shared memory as ONE 16-byte record {lx, ly, A, byte offset of the (y0,x0) cell | corner mask}
 //            (the reference redoes this set-up in every one of the D channel threads)
-//   phase 2  each lane walks its query's samples: LDS.64 + LDS.128 broadcast, then -- when all
-//            four corners are valid, the common case -- 4 unpredicated LDG.128 whose "+1 cell"
-//            addresses are immediate offsets (the cell stride is a template constant for
-//            Snipper's M*D = 384), 16 FFMA.  Border samples take a predicated slow path.
+//   phase 2  each lane walks its query's samples: one broadcast LDS.128, 8 FP instructions for the
+//            four corner weights, then -- when all four corners are valid, the common case -- 4
+//            unpredicated LDG.128 whose "+1 cell" addresses are immediate offsets (the cell stride is
+//            a template constant for Snipper's M*D = 384), 16 FFMA.  Border samples take a predicated
+//            slow path.
 //
 // Why this shape: ncu on the first versions (profiles/r01_run3_*, r01_run6_*) showed the gather
-// is limited first by INSTRUCTION ISSUE (64-bit address arithmetic, zero-filling registers for
+// limited first by INSTRUCTION ISSUE (64-bit address arithmetic, zero-filling registers for
 // predicated loads, per-corner predicate tests: ~93 instructions per lane-point for 16 useful
-// FFMA + 4 LDG) and then by the L1 data pipe (two 128-byte wavefronts per 192-byte head slice);
-// HBM traffic is only the compulsory ~42 MB per call.
+// FFMA + 4 LDG); once that was gone, by the L1 DATA PIPE (two 128-byte wavefronts per 192-byte head
+// slice, plus one per quarter warp for every wide shared load): the fused forward now runs at the
+// measured L1 gather ceiling (tools/micro/l1_tex_vs_ldg.cu).  HBM traffic is only the compulsory one.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -27,6 +27,7 @@
 
 namespace msda {
 
+// register form of a sample (unpacked from its record by record_meta)
 struct __align__(8) SampleMeta {
     int off;        // byte offset of cell (y0,x0) relative to (batch base + head slice), may be "virtual"
     unsigned wm;    // (row stride in bytes) | corner mask << 28
@@ -39,20 +40,34 @@ __device__ __forceinline__ int fast_div(int i, unsigned magic) { return (int)(((
 inline unsigned fast_magic(int d) { return (unsigned)(((1u << 24) + (unsigned)d - 1u) / (unsigned)d); }
 __device__ __forceinline__ unsigned fast_magic_dev(int d) { return ((1u << 24) + (unsigned)d - 1u) / (unsigned)d; }
 
-// Build the 8-byte meta word of a sample. cell_bytes = M*D*4 (bytes between consecutive cells).
-__device__ __forceinline__ SampleMeta make_meta(const Sample<float> &s, int W, int cell_bytes)
+// A sample is parked in shared memory as ONE 16-byte record {lx, ly, A, off | mask}: `off` is the byte
+// offset of the (y0,x0) cell -- a multiple of 16, so its low four bits carry the corner mask.  One
+// LDS.128 per sample and lane in the gather loop (wide shared loads cost an L1 wavefront per quarter
+// warp, and the L1 data pipe is what bounds these kernels); the row stride comes from the level table
+// and the four corner weights are recomputed per lane (8 FP instructions on otherwise idle issue slots).
+__device__ __forceinline__ float4 make_record(const Sample<float> &s, float at, int cell_bytes)
 {
-    SampleMeta m;
-    m.off = s.base * cell_bytes;
-    m.wm = (unsigned)(W * cell_bytes) | ((unsigned)s.mask << 28);
-    return m;
+    return make_float4(s.lx, s.ly, at, __int_as_float((s.base * cell_bytes) | s.mask));
 }
 
-__device__ __forceinline__ SampleMeta empty_meta()
+__device__ __forceinline__ float4 empty_record() { return make_float4(0.f, 0.f, 0.f, __int_as_float(0)); }
+
+// Unpack a record into the SampleMeta the gather helpers take (row = W_l * cell_bytes).
+__device__ __forceinline__ SampleMeta record_meta(const float4 &r, unsigned row)
 {
-    SampleMeta m;
-    m.off = 0; m.wm = 0u;
-    return m;
+    const int om = __float_as_int(r.w);
+    SampleMeta mt;
+    mt.off = om & ~15;
+    mt.wm = row | ((unsigned)(om & 15) << 28);
+    return mt;
+}
+
+// forward corner weights (bilinear x A) from a record
+__device__ __forceinline__ float4 record_weights(const float4 &r)
+{
+    const float hx = 1.f - r.x, hy = 1.f - r.y;
+    const float ah = hy * r.z, al = r.y * r.z;
+    return make_float4(ah * hx, ah * r.x, al * hx, al * r.x);
 }
 
 template <int CSB>

@@ -62,8 +62,7 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     using ET = typename C::elem;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *wts = reinterpret_cast<float4 *>(smem_raw);
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1));
+    float4 *rec = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, off | mask}, stride cl + 1 per query
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
@@ -88,28 +87,26 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = fast_div(i, magic_n);
             const int lp = lp0 + (i - spl * n);
-            SampleMeta mt = empty_meta();
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 r = empty_record();
             if (q0 + spl < a.Lq) {
                 const size_t si = (((size_t)nb * a.Lq + q0 + spl) * a.M + m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
-                const float at = __ldg(attn + si);
                 const int l = fast_div(lp, a.magic_P);
                 const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
-                mt = make_meta(s, lv.W[l], a.cell_bytes);
-                const float hx = 1.f - s.lx, hy = 1.f - s.ly;
-                w = make_float4(hy * hx * at, hy * s.lx * at, s.ly * hx * at, s.ly * s.lx * at);
+                r = make_record(s, __ldg(attn + si), a.cell_bytes);
             }
-            meta[i] = mt;
-            wts[i + spl] = w;  // 16-byte records are strided n + 1 per query: no LDS.128 bank conflicts
+            rec[i + spl] = r;
         }
         __syncthreads();
         // ---- phase 2: gather ----
         if (live) {
-            const SampleMeta *mm = meta + pl * n;
-            const float4 *ww = wts + pl * (n + 1);
+            const float4 *rr = rec + pl * (n + 1);
 #pragma unroll 4
-            for (int j = 0; j < n; ++j) gather_fma<VT, CSB>(acc, mm[j], ww[j], p0, a.cell_bytes);
+            for (int j = 0; j < n; ++j) {
+                const float4 r = rr[j];
+                const unsigned row = (unsigned)(lv.W[fast_div(lp0 + j, a.magic_P)] * a.cell_bytes);
+                gather_fma<VT, CSB>(acc, record_meta(r, row), record_weights(r), p0, a.cell_bytes);
+            }
         }
         if (lp0 + a.cl < LP) __syncthreads();  // staging buffers are reused by the next pass
     }
@@ -132,10 +129,8 @@ msda_bwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     constexpr int GS = 4 / (int)sizeof(ET);
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, -}
-    SampleMeta *meta = reinterpret_cast<SampleMeta *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1));
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1) +
-                                            sizeof(SampleMeta) * Cfg::PAIRS * a.cl);
+    float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, off | mask}, stride cl + 1 per query
+    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (a.cl + 1));
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
@@ -165,31 +160,28 @@ msda_bwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
         for (int i = tid; i < Cfg::PAIRS * n; i += Cfg::THREADS) {
             const int spl = fast_div(i, magic_n);
             const int lp = lp0 + (i - spl * n);
-            SampleMeta mt = empty_meta();
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 f = empty_record();
             if (q0 + spl < a.Lq) {
                 const size_t si = (((size_t)nb * a.Lq + q0 + spl) * a.M + m) * LP + lp;
                 const float2 uv = __ldg(reinterpret_cast<const float2 *>(loc) + si);
                 const int l = fast_div(lp, a.magic_P);
                 const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
-                mt = make_meta(s, lv.W[l], a.cell_bytes);
-                f = make_float4(s.lx, s.ly, __ldg(attn + si), 0.f);
+                f = make_record(s, __ldg(attn + si), a.cell_bytes);
             }
-            meta[i] = mt;
-            frac[i + spl] = f;  // stride n + 1 per query (bank-conflict-free LDS.128)
+            frac[i + spl] = f;
         }
         __syncthreads();
         // ---- phase 2: gather + scatter; every thread runs it (full-mask shuffles) ----
         {
-            const SampleMeta *mm = meta + pl * n;
             const float4 *ff = frac + pl * (n + 1);
             float *mypart = part + (size_t)(pl * n) * (Cfg::SUBS * 3) + sub * 3;
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
                 const float4 f = ff[j];
+                const SampleMeta mt = record_meta(f, (unsigned)(lv.W[fast_div(lp0 + j, a.magic_P)] * a.cell_bytes));
                 const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
                 float pa = 0.f, px = 0.f, py = 0.f;
-                gather_scatter<VT, CSB, SCATTER>(mm[j], bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
+                gather_scatter<VT, CSB, SCATTER>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
                 subgroup_sum3<Cfg::SUBG>(pa, px, py);
                 if ((lane & (Cfg::SUBG - 1)) == 0) {
                     float *dst = mypart + j * (Cfg::SUBS * 3);
@@ -269,7 +261,7 @@ static cudaError_t launch_fwd_fast(const typename Chunk<VT>::elem *value, const 
     using Cfg = FastCfg<LANES, PAIRS>;
     const FastArgs a = make_fast_args<VT, LANES, PAIRS>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
-    const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) + sizeof(SampleMeta) * Cfg::PAIRS * a.cl;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1);
     constexpr int C = snipper_csb<VT, LANES>();
     if (C != 0 && d.M * d.D == 384)
         msda_fwd_fast_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
@@ -287,8 +279,7 @@ static cudaError_t launch_bwd_fast(const typename Chunk<VT>::elem *value, const 
     using Cfg = FastCfg<LANES, PAIRS>;
     const FastArgs a = make_fast_args<VT, LANES, PAIRS>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
-    const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) +
-                        (sizeof(SampleMeta) + sizeof(float) * 3 * Cfg::SUBS) * Cfg::PAIRS * a.cl;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) + sizeof(float) * 3 * Cfg::SUBS * Cfg::PAIRS * a.cl;
     constexpr int C = snipper_csb<VT, LANES>();
     if (C != 0 && d.M * d.D == 384)
         msda_bwd_fast_kernel<VT, LANES, PAIRS, C, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(

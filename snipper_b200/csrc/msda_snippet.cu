@@ -83,7 +83,7 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es
         const int spl = fast_div(i, a.magic_LP);
         const int lp = i - spl * LP;
         const int q = q0 + spl;
-        float4 r = make_float4(0.f, 0.f, 0.f, __int_as_float(0));  // mask 0: inactive
+        float4 r = empty_record();  // mask 0: inactive
         if (q < d.Lq) {
             const float *e = es + spl * LP;
             float sum = 0.f;
@@ -96,21 +96,11 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es
             const float u = __ldg(rp) + o.x / (float)lv.W[l];
             const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
             const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
-            r = make_float4(s.lx, s.ly, at, __int_as_float((s.base * a.cell_bytes) | s.mask));
+            r = make_record(s, at, a.cell_bytes);
         }
         rec[i + spl] = r;  // records strided LP + 1 per query
     }
     __syncthreads();
-}
-
-// Unpack a record into the SampleMeta the gather helpers take (row = W_l * cell_bytes).
-__device__ __forceinline__ SampleMeta record_meta(const float4 &r, unsigned row)
-{
-    const int om = __float_as_int(r.w);
-    SampleMeta mt;
-    mt.off = om & ~15;
-    mt.wm = row | ((unsigned)(om & 15) << 28);
-    return mt;
 }
 
 // No occupancy floor in the launch bounds on purpose: given a register budget ptxas hoists loads
@@ -163,10 +153,7 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
         const unsigned row = (unsigned)(lv.W[l] * a.cell_bytes);
         for (int p = 0; p < d.P; ++p) {
             const float4 r = rr[l * d.P + p];
-            const float hx = 1.f - r.x, hy = 1.f - r.y;
-            const float ah = hy * r.z, al = r.y * r.z;
-            const float4 w = make_float4(ah * hx, ah * r.x, al * hx, al * r.x);
-            gather_fma_frames<VT, CSB>(acc, record_meta(r, row), w, pf, fstride, nf, a.cell_bytes);
+            gather_fma_frames<VT, CSB>(acc, record_meta(r, row), record_weights(r), pf, fstride, nf, a.cell_bytes);
         }
     }
     acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
