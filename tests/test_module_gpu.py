@@ -155,3 +155,27 @@ def test_unaliased_slots_fall_back_to_loop():
     assert mod._can_fuse(torch.empty(1, device=DEV))
     mod.sampling_offsets[1] = copy.deepcopy(mod.sampling_offsets[0])
     assert not mod._can_fuse(torch.empty(1, device=DEV))
+
+
+def test_fused_op_empty_and_single_frame_edge_cases():
+    """Degenerate shapes of the fused per-layer op: no queries, no batch, one frame, one query."""
+    import snipper_b200  # noqa: F401
+    shapes = torch.as_tensor([(5, 7), (3, 4)], dtype=torch.long, device=DEV)
+    lsi = torch.as_tensor([0, 35], dtype=torch.long, device=DEV)
+    S, M, D, L, P = 47, 8, 48, 2, 4
+
+    def call(N, T2, T1, Lq, n_frame):
+        value = torch.randn(N, T2, S, M, D, device=DEV)
+        off = torch.randn(N, T1, Lq, M, L, P, 2, device=DEV)
+        logits = torch.randn(N, T1, Lq, M, L, P, device=DEV)
+        ref = torch.rand(N, T1, Lq, L, 2, device=DEV)
+        return torch.ops.snipper_b200.snippet_forward(value, shapes, lsi, off, logits, ref, n_frame)
+
+    assert call(1, 4, 4, 0, 4).shape == (1, 4, 0, M * D)
+    assert call(0, 4, 4, 9, 4).shape == (0, 4, 9, M * D)
+    out = call(2, 1, 1, 1, 1)                      # T = 1: every query frame has exactly one neighbour
+    assert out.shape == (2, 1, 1, M * D) and torch.isfinite(out).all()
+    out = call(1, 3, 5, 33, 3)                     # two future query frames attend to all three source frames
+    assert out.shape == (1, 5, 33, M * D) and torch.isfinite(out).all()
+    with pytest.raises(RuntimeError):
+        call(1, 2, 2, 4, 3)                        # n_frame > T2
