@@ -111,6 +111,14 @@ MSDA_API size_t msda_backward_workspace_bytes(int batch, int spatial_size, int n
                                      unsigned flags);
 
 /*
+ * In-place masked zero-fill: data[i] = 0 where mask[i] != 0, i < n_elements (data: MSDA_DTYPE_F32 or
+ * MSDA_DTYPE_BF16, contiguous; mask: one byte per element, 16-byte aligned).  Replaces the out-of-place
+ * `value.masked_fill(input_padding_mask, 0)` of the reference module (ms_deform_attn.py:116-117) and its
+ * mirror on grad_value: only the mask is read and only masked elements are written.
+ */
+MSDA_API int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_elements, int dtype, void *stream);
+
+/*
  * Fused Snipper snippet attention (one launch per transformer layer).
  *   value            (N,T2,S,M,D)       element strides value_stride_n / value_stride_t
  *   offsets          (N,T1,Lq,M,L,P,2)  raw sampling_offsets Linear output, in pixels, contiguous

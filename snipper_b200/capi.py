@@ -28,7 +28,7 @@ MSDA_FLAG_ACCUMULATE_VALUE = 2
 # every symbol include/msda_b200.h declares
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_set_tuning", "msda_forward",
-    "msda_backward", "msda_backward_workspace_bytes", "msda_snippet_forward",
+    "msda_backward", "msda_backward_workspace_bytes", "msda_masked_zero", "msda_snippet_forward",
     "msda_snippet_backward",
 )
 
@@ -67,6 +67,8 @@ def lib():
     L.msda_backward.argtypes = [vp] * 9 + [i32] * 7 + [i64, i32, i32, u32, vp, sz, vp]
     L.msda_backward_workspace_bytes.restype = sz
     L.msda_backward_workspace_bytes.argtypes = [i32] * 8 + [u32]
+    L.msda_masked_zero.restype = i32
+    L.msda_masked_zero.argtypes = [vp, vp, i64, i32, vp]
     L.msda_snippet_forward.restype = i32
     L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 4 + [i32, vp]
     L.msda_snippet_backward.restype = i32

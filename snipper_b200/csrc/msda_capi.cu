@@ -220,6 +220,17 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
     return MSDA_OK;
 }
 
+int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_elements, int dtype, void *stream)
+{
+    if (n_elements < 0) return MSDA_ERR_INVALID_ARGUMENT;
+    if (n_elements == 0) return MSDA_OK;
+    if (!data || !mask) return MSDA_ERR_INVALID_ARGUMENT;
+    if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (!aligned16(mask)) return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_masked_zero(data, mask, n_elements, dtype == MSDA_DTYPE_BF16 ? 2 : 4,
+                                                static_cast<cudaStream_t>(stream)));
+}
+
 int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
                          const int64_t *level_start_index, const void *offsets, const void *logits,
                          const void *reference_points, void *output,

@@ -61,6 +61,9 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
                                               const OpDims &d, void *workspace, cudaStream_t stream,
                                               bool accumulate);
 
+// ---- in-place masked zero-fill (msda_mask.cu) ----
+cudaError_t launch_masked_zero(void *data, const uint8_t *mask, int64_t n, int elem_bytes, cudaStream_t stream);
+
 // ---- fused snippet op (msda_snippet.cu) ----
 bool snippet_ok(const SnippetDims &d);             // fp32
 bool snippet_ok(const SnippetDims &d, int esize);

@@ -108,8 +108,16 @@ class MSDeformAttn(nn.Module):
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
         value = self.value_proj(input_flatten)
+        value_mask = None
         if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask, 0.0)
+            if self._can_fuse(value) and ops.masked_zero_supported(value, input_padding_mask):
+                # in place on the projection's fresh output: reads the mask, writes only padded elements
+                # (the reference's masked_fill re-writes the whole tensor, :116-117); the fused op's
+                # backward zeroes the same elements of grad_value
+                value = ops.MaskedValue.apply(value, input_padding_mask)
+                value_mask = input_padding_mask
+            else:
+                value = value.masked_fill(input_padding_mask, 0.0)
         value = value.view(N, T2, S, M, self.d_model // M)
 
         if self._can_fuse(value):
@@ -119,7 +127,7 @@ class MSDeformAttn(nn.Module):
             logits = self.attention_weights[0](query).float().view(N, T1, Lq, M, L, P)
             out = torch.ops.snipper_b200.snippet_forward(
                 value, input_spatial_shapes, input_level_start_index, offsets, logits,
-                reference_points.float(), self.n_frame)
+                reference_points.float(), self.n_frame, value_mask)
             vis = self._vis_fused(offsets, logits, reference_points, input_spatial_shapes, T2) \
                 if self.attention_vis else None
         else:

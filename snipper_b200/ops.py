@@ -11,7 +11,7 @@ in the hand-written kernels.  Ops (namespace ``snipper_b200``):
 Both forwards carry ``register_autograd`` formulas, so they compose with autograd / DDP as plain
 nodes (no host sync, no unused parameters).
 """
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -219,6 +219,49 @@ msda_forward.register_autograd(_msda_backward_formula, setup_context=_msda_setup
 
 
 # ------------------------------------------------------------------------------------------
+# in-place masked zero-fill (value production)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("snipper_b200::masked_zero_", mutates_args=("data",))
+def masked_zero_(data: Tensor, mask: Tensor) -> None:
+    """data[i] = 0 where mask[i]; both contiguous, same shape; data float32 / bfloat16, mask bool."""
+    _require_cuda(data, "data")
+    _require_cuda(mask, "mask")
+    if data.shape != mask.shape or not data.is_contiguous() or not mask.is_contiguous():
+        raise RuntimeError("masked_zero_: data and mask must be contiguous tensors of one shape")
+    if mask.dtype != torch.bool or data.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("masked_zero_: data must be float32 / bfloat16 and mask bool")
+    with torch.cuda.device(data.device), _Launch("masked_zero", (data.numel(),), data.device):
+        st = capi.lib().msda_masked_zero(data.data_ptr(), mask.data_ptr(), data.numel(), _DTYPES[data.dtype],
+                                         _stream(data.device))
+    capi.check(st, "msda_masked_zero")
+
+
+def masked_zero_supported(data: Tensor, mask: Tensor) -> bool:
+    return (data.is_cuda and mask.is_cuda and data.dtype in (torch.float32, torch.bfloat16) and
+            mask.dtype == torch.bool and data.shape == mask.shape and data.is_contiguous() and
+            mask.is_contiguous() and mask.data_ptr() % 16 == 0)
+
+
+class MaskedValue(torch.autograd.Function):
+    """``value.masked_fill(mask, 0)`` done IN PLACE on the freshly produced projection output.
+
+    The backward is the identity ON PURPOSE: the only consumer of the result must be
+    ``snippet_forward(..., value_mask=mask)``, whose backward zeroes the masked elements of the
+    grad_value buffer it has just produced (same kernel, in place, no extra pass over the tensor).
+    Used only by the fused path of :class:`snipper_b200.modules.MSDeformAttn`."""
+
+    @staticmethod
+    def forward(ctx, value, mask):
+        torch.ops.snipper_b200.masked_zero_(value, mask)
+        ctx.mark_dirty(value)
+        return value
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad, None
+
+
+# ------------------------------------------------------------------------------------------
 # fused snippet op
 # ------------------------------------------------------------------------------------------
 def snippet_supported(n_heads: int, d_head: int, n_levels: int, n_points: int, dtype) -> bool:
@@ -272,7 +315,10 @@ def _ref_strides(ref):
 
 @torch.library.custom_op("snipper_b200::snippet_forward", mutates_args=())
 def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
-                    offsets: Tensor, logits: Tensor, reference_points: Tensor, n_frame: int) -> Tensor:
+                    offsets: Tensor, logits: Tensor, reference_points: Tensor, n_frame: int,
+                    value_mask: Optional[Tensor] = None) -> Tensor:
+    """``value_mask`` (bool, value's shape, contiguous) is not read here -- ``value`` must already be zero
+    where it is set (``MaskedValue``); it is carried to the backward, which zeroes those elements of grad_value."""
     N, T2, T1, S, M, D, L, Lq, P = _check_snippet(value, spatial_shapes, level_start_index, offsets,
                                                   logits, reference_points, n_frame)
     sn, st = _value_strides5(value)
@@ -289,7 +335,7 @@ def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Te
 
 
 @snippet_forward.register_fake
-def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame):
+def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame, value_mask=None):
     N, T2, S, M, D = value.shape
     return value.new_empty((N, offsets.shape[1], offsets.shape[2], M * D))
 
@@ -297,7 +343,7 @@ def _(value, spatial_shapes, level_start_index, offsets, logits, reference_point
 @torch.library.custom_op("snipper_b200::snippet_backward", mutates_args=())
 def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
                      offsets: Tensor, logits: Tensor, reference_points: Tensor, grad_output: Tensor,
-                     n_frame: int) -> Tuple[Tensor, Tensor, Tensor]:
+                     n_frame: int, value_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     N, T2, T1, S, M, D, L, Lq, P = _check_snippet(value, spatial_shapes, level_start_index, offsets,
                                                   logits, reference_points, n_frame)
     _require_cuda(grad_output, "grad_output")
@@ -315,32 +361,49 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
             _DTYPES[value.dtype], 0, _stream(value.device))
     capi.check(status, "msda_snippet_backward")
+    if value_mask is not None:
+        # d(masked_fill)/d(value) : no gradient reaches the masked elements (fresh buffer, in place)
+        if value_mask.dtype != torch.bool or value_mask.numel() != grad_value.numel() or not value_mask.is_contiguous():
+            raise RuntimeError("value_mask must be a contiguous bool tensor with value's number of elements")
+        with torch.cuda.device(value.device), _Launch("masked_zero", (grad_value.numel(),), value.device):
+            status = capi.lib().msda_masked_zero(grad_value.data_ptr(), value_mask.data_ptr(), grad_value.numel(),
+                                                 capi.MSDA_DTYPE_F32, _stream(value.device))
+        capi.check(status, "msda_masked_zero")
     if value.dtype != torch.float32:
         grad_value = grad_value.to(value.dtype)
     return grad_value, grad_offsets, grad_logits
 
 
 @snippet_backward.register_fake
-def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, grad_output, n_frame):
+def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, grad_output, n_frame, value_mask=None):
     return (value.new_empty(value.shape), torch.empty_like(offsets), torch.empty_like(logits))
 
 
 def _snippet_setup_context(ctx, inputs, output):
-    value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame = inputs
+    value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame, value_mask = inputs
     ctx.n_frame = n_frame
-    ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
+    ctx.has_mask = value_mask is not None
+    if ctx.has_mask:
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points, value_mask)
+    else:
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
 
 
 def _snippet_backward_formula(ctx, grad_output):
-    value, spatial_shapes, level_start_index, offsets, logits, ref = ctx.saved_tensors
+    if ctx.has_mask:
+        value, spatial_shapes, level_start_index, offsets, logits, ref, value_mask = ctx.saved_tensors
+    else:
+        value, spatial_shapes, level_start_index, offsets, logits, ref = ctx.saved_tensors
+        value_mask = None
     gv, goff, glog = torch.ops.snipper_b200.snippet_backward(
-        value, spatial_shapes, level_start_index, offsets, logits, ref, grad_output.contiguous(), ctx.n_frame)
+        value, spatial_shapes, level_start_index, offsets, logits, ref, grad_output.contiguous(), ctx.n_frame,
+        value_mask)
     gref = None
     if ctx.needs_input_grad[5]:
         # loc = ref + off/(W,H)  =>  dL/dref = sum_{m,p} dL/dloc = sum_{m,p} dL/doff * (W,H)
         wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
         gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
-    return gv, None, None, goff, glog, gref, None
+    return gv, None, None, goff, glog, gref, None, None
 
 
 snippet_forward.register_autograd(_snippet_backward_formula, setup_context=_snippet_setup_context)

@@ -179,3 +179,50 @@ def test_fused_op_empty_and_single_frame_edge_cases():
     assert out.shape == (1, 5, 33, M * D) and torch.isfinite(out).all()
     with pytest.raises(RuntimeError):
         call(1, 2, 2, 4, 3)                        # n_frame > T2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [0, 5, 16, 1000, 65536 + 7])
+def test_masked_zero_inplace_equals_masked_fill(dtype, n):
+    g = torch.Generator().manual_seed(n)
+    data = torch.randn(n, generator=g).to(dtype).to(DEV)
+    mask = (torch.rand(n, generator=g) < 0.3).to(DEV)
+    want = data.masked_fill(mask, 0.0)
+    torch.ops.snipper_b200.masked_zero_(data, mask)
+    assert torch.equal(data, want)
+
+
+def test_fused_module_with_padding_mask_matches_masked_fill_path():
+    """The in-place masked value production + masked grad_value of the fused path against the per-call loop,
+    which keeps the reference's out-of-place masked_fill (forward and every gradient)."""
+    shapes = torch.as_tensor([(9, 12), (5, 6), (3, 3)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    ours, _ = _pair(384, 8, 3, 4, 4, "encoder", seed=21)
+    loop = copy.deepcopy(ours)
+    loop.fused = False
+    g = torch.Generator().manual_seed(5)
+    N, T = 2, 4
+    q = torch.randn(N, T, S, 384, generator=g)
+    src = torch.randn(N, T, S, 384, generator=g)
+    refp = torch.rand(N, T, S, 3, 2, generator=g)
+    pix = torch.rand(N, T, S, 1, generator=g) < 0.25
+    mask = pix.expand(N, T, S, 384).contiguous()
+
+    def run(mod):
+        a = q.to(DEV).requires_grad_(True)
+        b = src.to(DEV).requires_grad_(True)
+        out = mod(a, refp.to(DEV), b, shapes.to(DEV), torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1])).to(DEV),
+                  mask.to(DEV))
+        out.square().sum().backward()
+        return out.detach(), a.grad, b.grad, [p.grad.clone() for p in mod.parameters()]
+
+    for m in (ours, loop):
+        m.zero_grad(set_to_none=True)
+    x = run(ours)
+    y = run(loop)
+    assert rel_err(x[0], y[0]) < 1e-5
+    assert rel_err(x[1], y[1]) < 1e-4 and rel_err(x[2], y[2]) < 1e-4
+    for gx, gy in zip(x[3], y[3]):
+        assert rel_err(gx, gy) < 1e-4
+    # the source rows under the padding mask feed nothing but the (zeroed) value: their gradient is exactly zero
+    assert float(x[2][pix.expand_as(x[2]).to(DEV)].abs().max()) == 0.0
