@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MSDA_API __attribute__((visibility("default")))
@@ -121,8 +121,13 @@ MSDA_API int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_e
 /*
  * Fused Snipper snippet attention (one launch per transformer layer).
  *   value            (N,T2,S,M,D)       element strides value_stride_n / value_stride_t
- *   offsets          (N,T1,Lq,M,L,P,2)  raw sampling_offsets Linear output, in pixels, contiguous
- *   logits           (N,T1,Lq,M,L,P)    raw attention_weights Linear output, contiguous
+ *   offsets          (N,T1,Lq,M,L,P,2)  raw sampling_offsets Linear output, in pixels
+ *   logits           (N,T1,Lq,M,L,P)    raw attention_weights Linear output
+ *                                       both dense per (n,t1,q) row; offsets_row_stride / logits_row_stride =
+ *                                       floats between consecutive rows (0 = dense), so the two may be column
+ *                                       blocks of ONE projection output (one GEMM instead of two)
+ *   offsets_bias     (M,L,P,2) or NULL  biases of the two Linear layers, added in-kernel (saves the GEMM
+ *   logits_bias      (M,L,P)   or NULL  epilogue pass over the projection output)
  *   reference_points (N,T1,Lq,L,2)      element strides ref_stride_n / ref_stride_t (0 allowed:
  *                                       the encoder expands one frame over T1)
  *   output           (N,T1,Lq,M*D)      contiguous
@@ -141,12 +146,15 @@ MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shap
                          int spatial_size, int num_heads, int channels, int num_levels,
                          int num_query, int num_point,
                          int64_t value_stride_n, int64_t value_stride_t,
-                         int64_t ref_stride_n, int64_t ref_stride_t, int dtype, void *stream);
+                         int64_t ref_stride_n, int64_t ref_stride_t,
+                         int64_t offsets_row_stride, int64_t logits_row_stride,
+                         const void *offsets_bias, const void *logits_bias, int dtype, void *stream);
 
 /*
  * grad_value (N,T2,S,M,D contiguous; zero-filled unless MSDA_FLAG_ACCUMULATE_VALUE),
- * grad_offsets like offsets, grad_logits like logits.  The gradient w.r.t. reference_points
- * is sum_{m,p} grad_offsets * (W_l,H_l) and is left to the caller.
+ * grad_offsets like offsets, grad_logits like logits (same row strides).  The gradient w.r.t.
+ * reference_points is sum_{m,p} grad_offsets * (W_l,H_l), the gradients of the biases are the sums of
+ * grad_offsets / grad_logits over rows; both are left to the caller.
  */
 MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           const int64_t *level_start_index, const void *offsets, const void *logits,
@@ -156,7 +164,9 @@ MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_sha
                           int spatial_size, int num_heads, int channels, int num_levels,
                           int num_query, int num_point,
                           int64_t value_stride_n, int64_t value_stride_t,
-                          int64_t ref_stride_n, int64_t ref_stride_t, int dtype, unsigned flags,
+                          int64_t ref_stride_n, int64_t ref_stride_t,
+                          int64_t offsets_row_stride, int64_t logits_row_stride,
+                          const void *offsets_bias, const void *logits_bias, int dtype, unsigned flags,
                           void *stream);
 
 #ifdef __cplusplus

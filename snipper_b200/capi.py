@@ -8,7 +8,7 @@ import os
 
 from .build import LIB_PATH
 
-MSDA_ABI_VERSION = 1
+MSDA_ABI_VERSION = 2
 
 MSDA_OK = 0
 MSDA_ERR_INVALID_ARGUMENT = 1
@@ -70,9 +70,9 @@ def lib():
     L.msda_masked_zero.restype = i32
     L.msda_masked_zero.argtypes = [vp, vp, i64, i32, vp]
     L.msda_snippet_forward.restype = i32
-    L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 4 + [i32, vp]
+    L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 6 + [vp, vp, i32, vp]
     L.msda_snippet_backward.restype = i32
-    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 4 + [i32, u32, vp]
+    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, i32, u32, vp]
     if L.msda_abi_version() != MSDA_ABI_VERSION:
         raise RuntimeError("libmsda_b200.so ABI %d != binding ABI %d; rebuild" %
                            (L.msda_abi_version(), MSDA_ABI_VERSION))

@@ -202,7 +202,8 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n_query_frames,
                         int n_frame, int spatial_size, int num_heads, int channels, int num_levels,
                         int num_query, int num_point, int64_t value_stride_n, int64_t value_stride_t,
-                        int64_t ref_stride_n, int64_t ref_stride_t, int dtype)
+                        int64_t ref_stride_n, int64_t ref_stride_t, int64_t offsets_row_stride,
+                        int64_t logits_row_stride, const void *offsets_bias, const void *logits_bias, int dtype)
 {
     if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
     if (batch < 0 || num_query < 0 || n_src_frames <= 0 || n_query_frames <= 0 || n_frame <= 0 ||
@@ -213,9 +214,15 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
     if (value_stride_n == 0) value_stride_n = value_stride_t * n_src_frames;
     if (value_stride_n < 0 || value_stride_t < 0 || ref_stride_n < 0 || ref_stride_t < 0)
         return MSDA_ERR_INVALID_ARGUMENT;
+    const int64_t mlp = (int64_t)num_heads * num_levels * num_point;
+    if (offsets_row_stride == 0) offsets_row_stride = 2 * mlp;
+    if (logits_row_stride == 0) logits_row_stride = mlp;
+    // float2 loads of the offsets need even row strides; rows must not overlap
+    if (offsets_row_stride < 2 * mlp || logits_row_stride < mlp || (offsets_row_stride & 1)) return MSDA_ERR_INVALID_ARGUMENT;
     d = msda::SnippetDims{batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
-                          value_stride_t, ref_stride_n, ref_stride_t};
+                          value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
+                          static_cast<const float *>(offsets_bias), static_cast<const float *>(logits_bias)};
     if (!msda::snippet_ok(d, dtype == MSDA_DTYPE_BF16 ? 2 : 4)) return MSDA_ERR_INVALID_ARGUMENT;
     return MSDA_OK;
 }
@@ -238,17 +245,21 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
                          int spatial_size, int num_heads, int channels, int num_levels,
                          int num_query, int num_point,
                          int64_t value_stride_n, int64_t value_stride_t,
-                         int64_t ref_stride_n, int64_t ref_stride_t, int dtype, void *stream)
+                         int64_t ref_stride_n, int64_t ref_stride_t,
+                         int64_t offsets_row_stride, int64_t logits_row_stride,
+                         const void *offsets_bias, const void *logits_bias, int dtype, void *stream)
 {
     msda::SnippetDims d;
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
-                          value_stride_t, ref_stride_n, ref_stride_t, dtype);
+                          value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
+                          offsets_bias, logits_bias, dtype);
     if (st != MSDA_OK) return st;
     if (batch == 0 || num_query == 0) return MSDA_OK;
     if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points || !output)
         return MSDA_ERR_INVALID_ARGUMENT;
-    if (!aligned16(value) || !aligned16(output) || !aligned16(offsets) || !aligned16(logits))
+    if (!aligned16(value) || !aligned16(output) || (reinterpret_cast<uintptr_t>(offsets) & 7u) ||
+        (reinterpret_cast<uintptr_t>(logits) & 3u) || (reinterpret_cast<uintptr_t>(offsets_bias) & 7u))
         return MSDA_ERR_INVALID_ARGUMENT;
     if (dtype == MSDA_DTYPE_BF16)
         return cuda_status(msda::launch_snippet_forward_bf16(
@@ -268,13 +279,16 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           int spatial_size, int num_heads, int channels, int num_levels,
                           int num_query, int num_point,
                           int64_t value_stride_n, int64_t value_stride_t,
-                          int64_t ref_stride_n, int64_t ref_stride_t, int dtype, unsigned flags,
+                          int64_t ref_stride_n, int64_t ref_stride_t,
+                          int64_t offsets_row_stride, int64_t logits_row_stride,
+                          const void *offsets_bias, const void *logits_bias, int dtype, unsigned flags,
                           void *stream)
 {
     msda::SnippetDims d;
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
-                          value_stride_t, ref_stride_n, ref_stride_t, dtype);
+                          value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
+                          offsets_bias, logits_bias, dtype);
     if (st != MSDA_OK) return st;
     if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_UNSUPPORTED_DTYPE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -288,7 +302,9 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
     if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points ||
         !grad_output || !grad_value || !grad_offsets || !grad_logits)
         return MSDA_ERR_INVALID_ARGUMENT;
-    if (!aligned16(value) || !aligned16(grad_output) || !aligned16(grad_value))
+    if (!aligned16(value) || !aligned16(grad_output) || !aligned16(grad_value) ||
+        (reinterpret_cast<uintptr_t>(offsets) & 7u) || (reinterpret_cast<uintptr_t>(grad_offsets) & 7u) ||
+        (reinterpret_cast<uintptr_t>(offsets_bias) & 7u))
         return MSDA_ERR_INVALID_ARGUMENT;
     if (dtype == MSDA_DTYPE_BF16)
         return cuda_status(msda::launch_snippet_backward_bf16(

@@ -18,6 +18,12 @@ struct SnippetDims {
     int N, T2, T1, n_frame, S, M, D, L, Lq, P;
     int64_t value_stride_n, value_stride_t;  // elements
     int64_t ref_stride_n, ref_stride_t;      // elements
+    // offsets / logits (and their gradients) may be column blocks of ONE projection output
+    // (the module runs both Linear layers as a single GEMM): floats between consecutive (n,t1,q) rows
+    int64_t off_row_stride, logit_row_stride;
+    // optional biases of the two Linear layers, added here instead of in a GEMM epilogue kernel
+    const float *off_bias;    // (M, L, P, 2) or nullptr
+    const float *logit_bias;  // (M, L, P) or nullptr
 };
 
 // ---- per-call op (msda_percall.cu) ----

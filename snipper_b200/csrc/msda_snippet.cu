@@ -69,7 +69,13 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
         const int spl = fast_div(i, a.magic_LP);
         const int q = q0 + spl;
-        zs[i] = q < d.Lq ? __ldg(logits + ((qbase + q) * d.M + m) * LP + (i - spl * LP)) : 0.f;
+        const int lp = i - spl * LP;
+        float z = 0.f;
+        if (q < d.Lq) {
+            z = __ldg(logits + (qbase + q) * d.logit_row_stride + m * LP + lp);
+            if (d.logit_bias != nullptr) z += __ldg(d.logit_bias + m * LP + lp);
+        }
+        zs[i] = z;
     }
     __syncthreads();
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
@@ -89,9 +95,12 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es
             float sum = 0.f;
             for (int j = 0; j < LP; ++j) sum += e[j];
             const float at = es[i] / sum * inv_k;
-            const size_t sp = (qbase + q) * d.M + m;
             const int l = fast_div(lp, a.magic_P);
-            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sp * LP + lp);
+            float2 o = __ldg(reinterpret_cast<const float2 *>(offsets + (qbase + q) * d.off_row_stride) + m * LP + lp);
+            if (d.off_bias != nullptr) {
+                const float2 b = __ldg(reinterpret_cast<const float2 *>(d.off_bias) + m * LP + lp);
+                o.x += b.x; o.y += b.y;
+            }
             const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
             const float u = __ldg(rp) + o.x / (float)lv.W[l];
             const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
@@ -248,8 +257,8 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
         if (q0 + spl < d.Lq) {
             // loc = ref + off/(W,H) and x = loc*W - 0.5  =>  dx/doff_x = 1: the W factor of the
             // per-call grad_loc (W*A*px) cancels against the 1/W of the normalisation.
-            const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
-            reinterpret_cast<float2 *>(grad_offsets)[si] = make_float2(at * px, at * py);
+            reinterpret_cast<float2 *>(grad_offsets + (qbase + q0 + spl) * d.off_row_stride)[m * LP + (i - spl * LP)] =
+                make_float2(at * px, at * py);
         }
         part[(size_t)i * (Cfg::SUBS * 3)] = pa * at;  // own slots only ([0] = gA_i A_i, [1] = gA_i)
         part[(size_t)i * (Cfg::SUBS * 3) + 1] = pa;
@@ -260,8 +269,8 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
         if (q0 + spl < d.Lq) {
             float dot = 0.f;
             for (int j = 0; j < LP; ++j) dot += part[(size_t)(spl * LP + j) * (Cfg::SUBS * 3)];
-            const size_t si = ((qbase + q0 + spl) * d.M + m) * LP + (i - spl * LP);
-            grad_logits[si] = frac[i + spl].z * (part[(size_t)i * (Cfg::SUBS * 3) + 1] - (float)nf * dot);
+            grad_logits[(qbase + q0 + spl) * d.logit_row_stride + m * LP + (i - spl * LP)] =
+                frac[i + spl].z * (part[(size_t)i * (Cfg::SUBS * 3) + 1] - (float)nf * dot);
         }
     }
 }

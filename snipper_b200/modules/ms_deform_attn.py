@@ -9,9 +9,9 @@ slots alias ONE Linear each, :68-71), same initialisation (:78-97), so checkpoin
 
 What differs is the execution:
 
-* fused path (default): offsets and logits are computed ONCE for all query frames (the
-  reference recomputes the same two GEMMs for every (t1,t2) pair -- 20 GEMMs per layer at T=4,
-  only 2 distinct), then ONE kernel launch per layer (``snipper_b200::snippet_forward``) does the
+* fused path (default): offsets and logits are computed ONCE for all query frames, by ONE GEMM
+  over the stacked weights (the reference recomputes the same two GEMMs for every (t1,t2) pair
+  -- 20 GEMMs per layer at T=4, only 2 distinct), then ONE kernel launch per layer (``snipper_b200::snippet_forward``) does the
   offset normalisation, the softmax over levels x points x neighbour frames and the gather from
   all neighbour frames.  No ``.contiguous()`` copies, no stack+sum, no host sync (the
   reference's shape assert at :112 synchronises the stream every call).
@@ -121,15 +121,23 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, T2, S, M, self.d_model // M)
 
         if self._can_fuse(value):
-            # value may be bf16 (autocast): the kernels gather bf16 and keep every location /
-            # weight computation in fp32, so offsets, logits and reference points go in as fp32
-            offsets = self.sampling_offsets[0](query).float().view(N, T1, Lq, M, L, P, 2)
-            logits = self.attention_weights[0](query).float().view(N, T1, Lq, M, L, P)
-            out = torch.ops.snipper_b200.snippet_forward(
-                value, input_spatial_shapes, input_level_start_index, offsets, logits,
+            # ONE GEMM for both per-query projections (the reference runs the two Linear layers once per
+            # (t1,t2) pair, :143-145,162-163): the weights are stacked [sampling_offsets | attention_weights],
+            # the biases are added inside the kernel (no GEMM epilogue pass over the projection output), and
+            # the kernel reads its offsets / logits as column blocks of the one output.
+            # value may be bf16 (autocast): the kernels gather bf16 and keep every location / weight
+            # computation in fp32, so the projection and the reference points go in as fp32.
+            so, aw = self.sampling_offsets[0], self.attention_weights[0]
+            proj = F.linear(query, torch.cat((so.weight, aw.weight), 0)).float()
+            out = torch.ops.snipper_b200.snippet_forward_packed(
+                value, input_spatial_shapes, input_level_start_index, proj, so.bias, aw.bias,
                 reference_points.float(), self.n_frame, value_mask)
-            vis = self._vis_fused(offsets, logits, reference_points, input_spatial_shapes, T2) \
-                if self.attention_vis else None
+            vis = None
+            if self.attention_vis:
+                n_off = so.weight.shape[0]
+                offsets = (proj[..., :n_off] + so.bias).view(N, T1, Lq, M, L, P, 2)
+                logits = (proj[..., n_off:] + aw.bias).view(N, T1, Lq, M, L, P)
+                vis = self._vis_fused(offsets, logits, reference_points, input_spatial_shapes, T2)
         else:
             out, vis = self._forward_per_call(query, reference_points, value, input_spatial_shapes,
                                               input_level_start_index)

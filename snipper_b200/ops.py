@@ -328,7 +328,7 @@ def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Te
         status = capi.lib().msda_snippet_forward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), out.data_ptr(),
-            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None,
             _DTYPES[value.dtype], _stream(value.device))
     capi.check(status, "msda_snippet_forward")
     return out
@@ -358,20 +358,24 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(),
-            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst,
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None,
             _DTYPES[value.dtype], 0, _stream(value.device))
     capi.check(status, "msda_snippet_backward")
+    _mask_grad_value(grad_value, value_mask, value.device)
+    if value.dtype != torch.float32:
+        grad_value = grad_value.to(value.dtype)
+    return grad_value, grad_offsets, grad_logits
+
+
+def _mask_grad_value(grad_value, value_mask, device):
     if value_mask is not None:
         # d(masked_fill)/d(value) : no gradient reaches the masked elements (fresh buffer, in place)
         if value_mask.dtype != torch.bool or value_mask.numel() != grad_value.numel() or not value_mask.is_contiguous():
             raise RuntimeError("value_mask must be a contiguous bool tensor with value's number of elements")
-        with torch.cuda.device(value.device), _Launch("masked_zero", (grad_value.numel(),), value.device):
+        with torch.cuda.device(device), _Launch("masked_zero", (grad_value.numel(),), device):
             status = capi.lib().msda_masked_zero(grad_value.data_ptr(), value_mask.data_ptr(), grad_value.numel(),
-                                                 capi.MSDA_DTYPE_F32, _stream(value.device))
+                                                 capi.MSDA_DTYPE_F32, _stream(device))
         capi.check(status, "msda_masked_zero")
-    if value.dtype != torch.float32:
-        grad_value = grad_value.to(value.dtype)
-    return grad_value, grad_offsets, grad_logits
 
 
 @snippet_backward.register_fake
@@ -407,3 +411,138 @@ def _snippet_backward_formula(ctx, grad_output):
 
 
 snippet_forward.register_autograd(_snippet_backward_formula, setup_context=_snippet_setup_context)
+
+
+# ------------------------------------------------------------------------------------------
+# fused snippet op, packed projection: offsets and logits are column blocks of ONE GEMM output and
+# the two Linear biases are added in-kernel (no second GEMM over the queries, no epilogue passes)
+# ------------------------------------------------------------------------------------------
+def _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref, n_frame):
+    for t, name in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                    (proj, "proj"), (ref, "reference_points")):
+        _require_cuda(t, name)
+    if value.dim() != 5 or proj.dim() != 4 or ref.dim() != 5:
+        raise RuntimeError("expected value (N,T2,S,M,D), proj (N,T1,Lq,3*M*L*P), reference_points (N,T1,Lq,L,2)")
+    N, T2, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Np, T1, Lq, W = proj.shape
+    if Np != N or W % (3 * M * L) != 0:
+        raise RuntimeError("proj must be (N,T1,Lq,3*M*L*P): [offsets (M,L,P,2) | logits (M,L,P)] per query")
+    P = W // (3 * M * L)
+    if tuple(ref.shape) != (N, T1, Lq, L, 2) or tuple(spatial_shapes.shape) != (L, 2):
+        raise RuntimeError("reference_points must be (N,T1,Lq,L,2) and spatial_shapes (L,2)")
+    if not snippet_supported(M, D, L, P, value.dtype):
+        raise RuntimeError("fused snippet attention needs float32 / bfloat16 value, D % 16 == 0, D <= 128, L*P <= 32")
+    if proj.dtype != torch.float32 or ref.dtype != torch.float32:
+        raise RuntimeError("proj and reference_points must be float32")
+    for b, n in ((offsets_bias, 2 * M * L * P), (logits_bias, M * L * P)):
+        if b is not None and (not b.is_cuda or b.dtype != torch.float32 or b.numel() != n or not b.is_contiguous()):
+            raise RuntimeError("biases must be contiguous float32 CUDA tensors of 2*M*L*P / M*L*P elements")
+    if not (0 < n_frame <= T2):
+        raise RuntimeError("n_frame must be in (0, T2]")
+    _require_contiguous(proj, "proj")
+    _require_contiguous(spatial_shapes, "spatial_shapes")
+    _require_contiguous(level_start_index, "level_start_index")
+    return N, T2, T1, S, M, D, L, Lq, P
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+@torch.library.custom_op("snipper_b200::snippet_forward_packed", mutates_args=())
+def snippet_forward_packed(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, proj: Tensor,
+                           offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
+                           reference_points: Tensor, n_frame: int, value_mask: Optional[Tensor] = None) -> Tensor:
+    N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
+                                                 logits_bias, reference_points, n_frame)
+    sn, st = _value_strides5(value)
+    ref, rsn, rst = _ref_strides(reference_points)
+    mlp = M * L * P
+    out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device), _Launch("snippet_forward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
+        status = capi.lib().msda_snippet_forward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), out.data_ptr(),
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
+            _ptr(offsets_bias), _ptr(logits_bias), _DTYPES[value.dtype], _stream(value.device))
+    capi.check(status, "msda_snippet_forward")
+    return out
+
+
+@snippet_forward_packed.register_fake
+def _(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points, n_frame,
+      value_mask=None):
+    N, T2, S, M, D = value.shape
+    return value.new_empty((N, proj.shape[1], proj.shape[2], M * D))
+
+
+@torch.library.custom_op("snipper_b200::snippet_backward_packed", mutates_args=())
+def snippet_backward_packed(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, proj: Tensor,
+                            offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
+                            reference_points: Tensor, grad_output: Tensor, n_frame: int,
+                            value_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Returns (grad_value, grad_proj): grad_proj has proj's layout [grad_offsets | grad_logits]."""
+    N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
+                                                 logits_bias, reference_points, n_frame)
+    _require_cuda(grad_output, "grad_output")
+    _require_contiguous(grad_output, "grad_output")
+    sn, st = _value_strides5(value)
+    ref, rsn, rst = _ref_strides(reference_points)
+    mlp = M * L * P
+    grad_value = torch.empty((N, T2, S, M, D), dtype=torch.float32, device=value.device)  # fp32 accumulation
+    grad_proj = torch.empty_like(proj)
+    with torch.cuda.device(value.device), _Launch("snippet_backward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
+        status = capi.lib().msda_snippet_backward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
+            _ptr(offsets_bias), _ptr(logits_bias), _DTYPES[value.dtype], 0, _stream(value.device))
+    capi.check(status, "msda_snippet_backward")
+    _mask_grad_value(grad_value, value_mask, value.device)
+    if value.dtype != torch.float32:
+        grad_value = grad_value.to(value.dtype)
+    return grad_value, grad_proj
+
+
+@snippet_backward_packed.register_fake
+def _(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points, grad_output,
+      n_frame, value_mask=None):
+    return value.new_empty(value.shape), torch.empty_like(proj)
+
+
+def _packed_setup_context(ctx, inputs, output):
+    value, spatial_shapes, level_start_index, proj, ob, lb, reference_points, n_frame, value_mask = inputs
+    ctx.n_frame = n_frame
+    ctx.flags = (ob is not None, lb is not None, value_mask is not None)
+    ctx.save_for_backward(*[t for t in (value, spatial_shapes, level_start_index, proj, reference_points, ob, lb,
+                                        value_mask) if t is not None])
+
+
+def _packed_backward_formula(ctx, grad_output):
+    saved = list(ctx.saved_tensors)
+    value, spatial_shapes, level_start_index, proj, ref = saved[:5]
+    rest = saved[5:]
+    ob = rest.pop(0) if ctx.flags[0] else None
+    lb = rest.pop(0) if ctx.flags[1] else None
+    value_mask = rest.pop(0) if ctx.flags[2] else None
+    gv, gproj = torch.ops.snipper_b200.snippet_backward_packed(
+        value, spatial_shapes, level_start_index, proj, ob, lb, ref, grad_output.contiguous(), ctx.n_frame, value_mask)
+    N, T2, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    mlp = proj.shape[-1] // 3
+    P = mlp // (M * L)
+    gob = glb = gref = None
+    if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+        col = gproj.sum(dim=(0, 1, 2))                       # bias gradients = column sums of the projection gradient
+        gob = col[:2 * mlp] if ctx.needs_input_grad[4] else None
+        glb = col[2 * mlp:] if ctx.needs_input_grad[5] else None
+    if ctx.needs_input_grad[6]:
+        goff = gproj[..., :2 * mlp].view(proj.shape[0], proj.shape[1], proj.shape[2], M, L, P, 2)
+        wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
+        gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
+    return gv, None, None, gproj, gob, glb, gref, None, None
+
+
+snippet_forward_packed.register_autograd(_packed_backward_formula, setup_context=_packed_setup_context)
