@@ -281,12 +281,18 @@ static cudaError_t launch_bwd_fast(const typename Chunk<VT>::elem *value, const 
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (a.cl + 1) + sizeof(float) * 3 * Cfg::SUBS * Cfg::PAIRS * a.cl;
     constexpr int C = snipper_csb<VT, LANES>();
-    if (C != 0 && d.M * d.D == 384)
+    if (C != 0 && d.M * d.D == 384) {
         msda_bwd_fast_kernel<VT, LANES, PAIRS, C, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
-    else
+    } else {
+        if (smem > 48 * 1024) {  // wide heads x many samples per pass (D = 128, L*P = 32: 57.6 KB)
+            const cudaError_t e = cudaFuncSetAttribute(msda_bwd_fast_kernel<VT, LANES, PAIRS, 0, SCATTER>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         msda_bwd_fast_kernel<VT, LANES, PAIRS, 0, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
+    }
     return cudaGetLastError();
 }
 

@@ -42,6 +42,17 @@ def test_bf16_percall_vs_oracle(D, regime):
     assert rel_err(ga, ref_ga) < F32_BWD_TOL
 
 
+def test_bf16_wide_heads_many_samples():
+    """D = 128 with L*P = 32 samples per query: the backward needs more than 48 KB of dynamic shared memory."""
+    c = make_case(1, 2, 128, [(9, 12), (5, 6), (3, 3), (2, 2)], 8, Lq=37, regime="uniform", seed=9)
+    c["value"], c["grad_out"] = c["value"].bfloat16(), c["grad_out"].bfloat16()
+    out, (gv, gl, ga) = cuda_fwd_bwd(c["value"], c["shapes"], c["lsi"], c["loc"], c["attn"], c["grad_out"])
+    args = (c["value"].double(), c["shapes"], c["lsi"], c["loc"].double(), c["attn"].double())
+    ref_gv, ref_gl, ref_ga = c_oracle.backward(*args, c["grad_out"].double())
+    assert rel_err(out, c_oracle.forward(*args)) < BF16_TOL
+    assert rel_err(gv, ref_gv) < BF16_TOL and rel_err(gl, ref_gl) < F32_BWD_TOL and rel_err(ga, ref_ga) < F32_BWD_TOL
+
+
 def test_bf16_output_is_the_rounded_fp32_result():
     """Same inputs through the fp32 kernels: the bf16 kernel's output is that result rounded once."""
     c = _bf16_case(1, 8, 48, 4, None, "local", seed=5)

@@ -1,0 +1,84 @@
+"""Seeded shape fuzzing of the CUDA path against the C oracle: random level pyramids, head counts, channel
+widths (fast and generic kernels), point counts, ragged query counts, batch strides, out-of-range samples.
+Forward <= 1e-5, backward <= 1e-4 relative (fp32), as everywhere."""
+import random
+
+import pytest
+import torch
+
+from conftest import level_start_index, rel_err
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _random_case(rng):
+    L = rng.choice([1, 2, 3, 4, 6])
+    shapes = torch.as_tensor([(rng.randint(1, 14), rng.randint(1, 14)) for _ in range(L)], dtype=torch.long)
+    M = rng.choice([1, 2, 3, 8])
+    D = rng.choice([4, 8, 16, 20, 32, 48, 48, 64, 100, 128])
+    P = rng.choice([1, 2, 4, 5, 8])
+    N = rng.choice([1, 2, 3])
+    Lq = rng.choice([1, 7, 16, 17, 60, 131])
+    S = int(shapes.prod(1).sum())
+    g = torch.Generator().manual_seed(rng.randint(0, 1 << 30))
+    value = torch.randn(N, S, M, D, generator=g)
+    spread = rng.choice([0.2, 1.0, 3.0])            # > 1: a good share of the samples falls outside [0,1]
+    loc = 0.5 + (torch.rand(N, Lq, M, L, P, 2, generator=g) - 0.5) * (1.0 + spread)
+    attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    go = torch.randn(N, Lq, M * D, generator=g)
+    return dict(value=value, shapes=shapes, lsi=level_start_index(shapes), loc=loc, attn=attn, grad_out=go,
+                strided=rng.random() < 0.3)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_per_call(seed):
+    from snipper_b200 import MSDeformAttnFunction
+    rng = random.Random(1000 + seed)
+    c = _random_case(rng)
+    v = c["value"].to(DEV)
+    if c["strided"] and v.shape[0] > 1:             # value[:, t] of a frame-stacked tensor: batch stride != S*M*D
+        big = torch.zeros(v.shape[0], 2, *v.shape[1:], device=DEV)
+        big[:, 1] = v
+        v = big[:, 1]
+    v = v.detach().requires_grad_(True)
+    s = c["loc"].to(DEV).requires_grad_(True)
+    a = c["attn"].to(DEV).requires_grad_(True)
+    out = MSDeformAttnFunction.apply(v, c["shapes"].to(DEV), c["lsi"].to(DEV), s, a, 64)
+    out.backward(c["grad_out"].to(DEV))
+    args = (c["value"].double(), c["shapes"], c["lsi"], c["loc"].double(), c["attn"].double())
+    ref_out = c_oracle.forward(*args)
+    ref = c_oracle.backward(*args, c["grad_out"].double())
+    assert rel_err(out, ref_out) < 1e-5
+    for got, want in zip((v.grad, s.grad, a.grad), ref):
+        assert rel_err(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_fused_vs_per_call(seed):
+    """Fused per-layer op on random geometry against T1 x |neighbours| per-call launches (oracle-checked above)."""
+    rng = random.Random(2000 + seed)
+    L = rng.choice([1, 2, 3])
+    shapes = torch.as_tensor([(rng.randint(2, 10), rng.randint(2, 10)) for _ in range(L)], dtype=torch.long, device=DEV)
+    lsi = level_start_index(shapes.cpu()).to(DEV)
+    S = int(shapes.prod(1).sum())
+    M, D, P = rng.choice([(8, 48, 4), (4, 32, 2), (2, 64, 8), (8, 16, 4)])
+    N, n_frame, fut = rng.choice([1, 2]), rng.choice([1, 2, 4]), rng.choice([0, 1, 2])
+    T2, T1, Lq = n_frame, n_frame + fut, rng.choice([1, 9, 33])
+    g = torch.Generator().manual_seed(seed)
+    value = torch.randn(N, T2, S, M, D, generator=g).to(DEV)
+    off = (torch.randn(N, T1, Lq, M, L, P, 2, generator=g) * 2.0).to(DEV)
+    logits = torch.randn(N, T1, Lq, M, L, P, generator=g).to(DEV)
+    ref = (torch.rand(N, T1, Lq, L, 2, generator=g) * 1.2 - 0.1).to(DEV)
+    got = torch.ops.snipper_b200.snippet_forward(value, shapes, lsi, off, logits, ref, n_frame)
+    wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
+    loc = ref[:, :, :, None, :, None, :] + off / wh[None, None, None, None, :, None, :]
+    att = torch.softmax(logits.flatten(-2), -1).view(N, T1, Lq, M, L, P)
+    want = torch.zeros_like(got)
+    for t1 in range(T1):
+        nb = [t for t in (t1 - 1, t1, t1 + 1) if 0 <= t < n_frame] if t1 < n_frame else list(range(T2))
+        for t2 in nb:
+            want[:, t1] += torch.ops.snipper_b200.msda_forward(value[:, t2], shapes, lsi, loc[:, t1].contiguous(),
+                                                               (att[:, t1] / len(nb)).contiguous(), 64)
+    assert rel_err(got, want) < 1e-5
