@@ -82,3 +82,69 @@ def test_random_shapes_fused_vs_per_call(seed):
             want[:, t1] += torch.ops.snipper_b200.msda_forward(value[:, t2], shapes, lsi, loc[:, t1].contiguous(),
                                                                (att[:, t1] / len(nb)).contiguous(), 64)
     assert rel_err(got, want) < 1e-5
+
+
+def _composition(value, shapes, lsi, off, logits, ref, n_frame):
+    """The fused op written out with per-call launches and torch glue (differentiable)."""
+    from snipper_b200 import MSDeformAttnFunction
+    N, T2 = value.shape[:2]
+    _, T1, Lq, M, L, P, _ = off.shape
+    wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(off.dtype)
+    loc = ref[:, :, :, None, :, None, :] + off / wh[None, None, None, None, :, None, :]
+    att = torch.softmax(logits.flatten(-2), -1).view(N, T1, Lq, M, L, P)
+    outs = []
+    for t1 in range(T1):
+        nb = [t for t in (t1 - 1, t1, t1 + 1) if 0 <= t < n_frame] if t1 < n_frame else list(range(T2))
+        acc = 0
+        for t2 in nb:
+            acc = acc + MSDeformAttnFunction.apply(value[:, t2], shapes, lsi, loc[:, t1].contiguous(),
+                                                   (att[:, t1] / len(nb)).contiguous(), 64)
+        outs.append(acc)
+    return torch.stack(outs, 1)
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_random_shapes_fused_backward_vs_composition(seed, dtype):
+    rng = random.Random(3000 + seed)
+    L = rng.choice([1, 2, 3])
+    shapes = torch.as_tensor([(rng.randint(2, 9), rng.randint(2, 9)) for _ in range(L)], dtype=torch.long, device=DEV)
+    lsi = level_start_index(shapes.cpu()).to(DEV)
+    S = int(shapes.prod(1).sum())
+    M, D, P = rng.choice([(8, 48, 4), (4, 32, 2), (2, 64, 8), (8, 16, 4), (2, 128, 8)])
+    N, n_frame, fut = rng.choice([1, 2]), rng.choice([1, 2, 4]), rng.choice([0, 1, 2])
+    T2, T1, Lq = n_frame, n_frame + fut, rng.choice([1, 9, 33])
+    g = torch.Generator().manual_seed(100 + seed)
+    value = torch.randn(N, T2, S, M, D, generator=g).to(dtype)
+    off = torch.randn(N, T1, Lq, M, L, P, 2, generator=g) * 2.0
+    logits = torch.randn(N, T1, Lq, M, L, P, generator=g)
+    ref = torch.rand(N, T1, Lq, L, 2, generator=g) * 1.2 - 0.1
+    go = torch.randn(N, T1, Lq, M * D, generator=g).to(dtype)
+
+    def run(fn):
+        leaves = [t.to(DEV).requires_grad_(True) for t in (value, off, logits, ref)]
+        out = fn(leaves[0], shapes, lsi, leaves[1], leaves[2], leaves[3], n_frame)
+        out.backward(go.to(DEV))
+        return [out.detach()] + [t.grad for t in leaves]
+
+    a = run(lambda *x: torch.ops.snipper_b200.snippet_forward(*x))
+    b = run(_composition)
+    ftol, vtol = (1e-5, 1e-4) if dtype == torch.float32 else (1e-2, 1e-2)
+    assert rel_err(a[0], b[0]) < ftol
+    assert rel_err(a[1], b[1]) < vtol            # grad_value
+    for i in (2, 3, 4):                          # grad_offsets, grad_logits, grad_reference_points (fp32 in both modes)
+        assert rel_err(a[i], b[i]) < (1e-4 if dtype == torch.float32 else 2e-2), i
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_shapes_deterministic_backward(seed):
+    """Deterministic mode on random geometry: equals the oracle and is bit-identical run to run."""
+    rng = random.Random(4000 + seed)
+    c = _random_case(rng)
+    dev_args = [c[k].to(DEV) for k in ("value", "shapes", "lsi", "loc", "attn", "grad_out")]
+    a = torch.ops.snipper_b200.msda_backward(*dev_args, 64, True)
+    b = torch.ops.snipper_b200.msda_backward(*dev_args, 64, True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    args = (c["value"].double(), c["shapes"], c["lsi"], c["loc"].double(), c["attn"].double())
+    for got, want in zip(a, c_oracle.backward(*args, c["grad_out"].double())):
+        assert rel_err(got, want) < 1e-4
