@@ -106,7 +106,8 @@ def main():
             "batch_per_gpu": args.batch, "dtype": "bf16-autocast" if args.bf16 else "f32",
             "parallelism": "DDP x%d (NCCL gradient all-reduce, 171 MB fp32 per step)" % world if world > 1 else "single GPU",
             "msda_ms_per_step": msda_ms, "msda_share": msda_ms / (ms / args.steps),
-            "msda_kernels_ms_per_step": {"%s Lq=%d T1=%d" % (k[0], k[1][7], k[1][2]): round(sum(v) / 2, 3) for k, v in per.items()},
+            "msda_kernels_ms_per_step": {("%s Lq=%d T1=%d" % (k[0], k[1][7], k[1][2])) if len(k[1]) >= 8 else k[0]: round(sum(v) / 2, 3)
+                                         for k, v in per.items()},
             "final_loss": float(loss.detach()), "data": "synthetic", "loss": "synthetic dense loss over all heads"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
