@@ -194,14 +194,14 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
     def fwd():
         r = L.msda_snippet_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                    logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
-                                   Lv, Lq, P, 0, 0, rs[0], rs[1], dt, st)
+                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, dt, st)
         assert r == 0, r
 
     def bwd():
         r = L.msda_snippet_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], dt, 0, st)
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, dt, 0, st)
         assert r == 0, r
 
     e = 2 if bf16 else 4   # value / output / grad_output element size; everything else is fp32
