@@ -101,7 +101,9 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
         // ---- phase 2: gather ----
         if (live) {
             const float4 *rr = rec + pl * (n + 1);
-#pragma unroll 4
+            // fp32 lanes: unroll 2 = 40 registers / 8 CTAs per SM (unroll 4 takes 54 and loses two resident
+            // CTAs: 3 % slower at N = 8); the bf16 lane types measured better with 4 (profiles/r01_run44_*)
+#pragma unroll (sizeof(ET) == 4 ? 2 : 4)
             for (int j = 0; j < n; ++j) {
                 const float4 r = rr[j];
                 const unsigned row = (unsigned)(lv.W[fast_div(lp0 + j, a.magic_P)] * a.cell_bytes);
