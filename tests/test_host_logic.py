@@ -42,6 +42,34 @@ def test_argument_validation_needs_no_gpu():
     assert L.msda_backward_workspace_bytes(1, 100, 8, 48, 3, 100, 4, 0, capi.MSDA_FLAG_DETERMINISTIC) > 0
 
 
+def test_fused_and_mask_entry_points_validate_without_a_gpu():
+    L = capi.lib()
+    F32, BF16, F64 = capi.MSDA_DTYPE_F32, capi.MSDA_DTYPE_BF16, capi.MSDA_DTYPE_F64
+    # msda_masked_zero: empty is a no-op, null pointers / bad dtype / misaligned mask are rejected
+    assert L.msda_masked_zero(0, 0, 0, F32, 0) == capi.MSDA_OK
+    assert L.msda_masked_zero(0, 0, 16, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert L.msda_masked_zero(256, 256, 16, F64, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert L.msda_masked_zero(256, 257, 16, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
+    # msda_snippet_forward(value, shapes, lsi, offsets, logits, ref, out, N,T2,T1,n_frame,S,M,D,L,Lq,P, strides x6, biases x2, dtype, stream)
+    def fwd(N=1, T2=4, T1=4, n_frame=4, S=100, M=8, D=48, Lv=3, Lq=10, P=4, ors=0, lrs=0, dtype=F32, ptr=256):
+        return L.msda_snippet_forward(ptr, ptr, ptr, ptr, ptr, ptr, ptr, N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
+                                      0, 0, 0, 0, ors, lrs, None, None, dtype, 0)
+    assert fwd(N=0) == capi.MSDA_OK and fwd(Lq=0) == capi.MSDA_OK          # empty problems: nothing is launched
+    assert fwd(n_frame=5) == capi.MSDA_ERR_INVALID_ARGUMENT                 # n_frame > T2
+    assert fwd(D=40) == capi.MSDA_ERR_INVALID_ARGUMENT                      # D % 16 != 0
+    assert fwd(Lv=9, P=4) == capi.MSDA_ERR_INVALID_ARGUMENT                 # L*P > 32
+    assert fwd(dtype=F64) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert fwd(ors=8 * 3 * 4 * 2 - 2) == capi.MSDA_ERR_INVALID_ARGUMENT     # rows would overlap
+    assert fwd(ors=8 * 3 * 4 * 3 + 1) == capi.MSDA_ERR_INVALID_ARGUMENT     # odd row stride breaks the float2 loads
+    assert fwd(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT                     # null pointers with work to do
+    # deterministic mode is per-call only
+    assert L.msda_snippet_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 4, 4, 4, 100, 8, 48, 3, 10, 4,
+                                   0, 0, 0, 0, 0, 0, None, None, F32, capi.MSDA_FLAG_DETERMINISTIC, 0) \
+        == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    # bf16 needs D % 16 == 0 in the per-call entry points too
+    assert L.msda_forward(256, 256, 256, 256, 256, 256, 1, 4, 2, 24, 1, 3, 2, 0, 64, BF16, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+
+
 def test_cpu_tensors_raise_like_the_reference():
     shim = snipper_b200.install_extension_shim()
     args = (torch.zeros(1, 4, 2, 16), torch.tensor([[2, 2]]), torch.tensor([0]),
