@@ -4,6 +4,7 @@
 #include "../../include/msda_b200.h"
 #include "msda_internal.h"
 
+#include <stdint.h>
 #include <string.h>
 
 namespace msda {
@@ -145,6 +146,11 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     st = check_im2col_step(batch, im2col_step);
     if (st != MSDA_OK) return st;
     if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_F64 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    // corner ids / cell ids of the deterministic two-pass mode are 32-bit (checked before anything is enqueued)
+    if ((flags & MSDA_FLAG_DETERMINISTIC) &&
+        ((int64_t)batch * num_query * num_heads * num_levels * num_point * 4 >= (int64_t)INT32_MAX ||
+         (int64_t)batch * spatial_size * num_heads >= (int64_t)INT32_MAX))
+        return MSDA_ERR_TOO_LARGE;
     if (value_batch_stride == 0) value_batch_stride = (int64_t)spatial_size * num_heads * channels;
     if (value_batch_stride < 0) return MSDA_ERR_INVALID_ARGUMENT;
     msda::OpDims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, value_batch_stride};

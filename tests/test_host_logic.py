@@ -66,6 +66,9 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert L.msda_snippet_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 4, 4, 4, 100, 8, 48, 3, 10, 4,
                                    0, 0, 0, 0, 0, 0, None, None, F32, capi.MSDA_FLAG_DETERMINISTIC, 0) \
         == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    # deterministic mode: 32-bit corner ids -> a clear error instead of a wrong answer
+    assert L.msda_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 64, 9875, 8, 48, 12, 9875 * 4, 8, 0, 64, F32,
+                           capi.MSDA_FLAG_DETERMINISTIC, 256, 1 << 40, 0) == capi.MSDA_ERR_TOO_LARGE
     # bf16 needs D % 16 == 0 in the per-call entry points too
     assert L.msda_forward(256, 256, 256, 256, 256, 256, 1, 4, 2, 24, 1, 3, 2, 0, 64, BF16, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
 
