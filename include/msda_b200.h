@@ -17,6 +17,9 @@
  *   msda_snippet_backward      models/ops/modules/ms_deform_attn.py:126-225 (offset normalisation,
  *                              softmax over levels x points x neighbour frames, one op call per
  *                              (t1,t2) pair, sum over t2) fused into one launch per layer
+ *   msda_frame_sum /        <- value.masked_fill(input_padding_mask, 0) (ms_deform_attn.py:116-117) and
+ *   msda_frame_unsum           the stack(-1).sum(-1) over neighbour frames (:225), moved IN FRONT of the
+ *                              gather by linearity of the op in `value` (one gather per query frame)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer; the caller owns every buffer; the library allocates
@@ -28,7 +31,13 @@
  *     [0,1] incl. padding; attn_weight (N,Lq,M,L,P); output (N,Lq,M*D).
  *   - every function returns an msda_status_t (0 = ok).  Launch failures are returned, not
  *     printed (the reference only printf()s them, ms_deform_im2col_cuda.cuh:948-952).
- *   - re-entrant and stateless.
+ *   - re-entrant and stateless: no entry point writes process state.  (Two benchmark knobs are READ
+ *     from the environment once, at the first launch: MSDA_PAIRS_D48 / MSDA_SNIP_PAIRS_D48 = 8|16|32,
+ *     queries per CTA tile for D = 48; results never depend on them.)
+ *   - padding masks: one byte per element, != 0 = padding; element (n,t,s,c) of a mask over value
+ *     (N,T2,S,M*D) lives at mask[((n*T2+t)*S+s)*mask_row_stride + c*mask_col_stride] with
+ *     mask_col_stride 1 (the reference's materialised (N,T,S,C) bool tensor, models/model.py:156-157;
+ *     needs mask 4-byte aligned and mask_row_stride % 4 == 0) or 0 (one byte per pixel).
  */
 #ifndef MSDA_B200_H_
 #define MSDA_B200_H_
@@ -40,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 2
+#define MSDA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MSDA_API __attribute__((visibility("default")))
@@ -67,17 +76,17 @@ typedef enum {
                            (MSDA_ERR_UNSUPPORTED_DTYPE otherwise); no deterministic mode. */
 } msda_dtype_t;
 
-/* msda_backward / msda_snippet_backward flags */
+/* flags of msda_backward / msda_snippet_forward / msda_snippet_backward */
 #define MSDA_FLAG_DETERMINISTIC 1u   /* two-pass, atomics-free grad_value (needs workspace)   */
 #define MSDA_FLAG_ACCUMULATE_VALUE 2u /* add into grad_value instead of zero-filling it first */
+#define MSDA_FLAG_PRESUMMED 4u       /* snippet entries: `value` / `grad_value` hold one neighbour-frame
+                                        SUM per query-frame slot, (N, msda_snippet_num_slots(), S, M, D),
+                                        as written by msda_frame_sum / consumed by msda_frame_unsum    */
 
 MSDA_API int msda_abi_version(void);
 MSDA_API const char *msda_error_string(int status);
 /* cudaError_t of the last failed launch seen by this thread (0 if none). */
 MSDA_API int msda_last_cuda_error(void);
-/* Optional performance knob (results never depend on it): queries per CTA tile for D = 48.
- * keys "pairs_d48" (per-call kernels) and "snip_pairs_d48" (fused kernels); value 8, 16 or 32. */
-MSDA_API int msda_set_tuning(const char *key, int value);
 
 /*
  * Forward.  output[n,q,m*D+c] = sum_{l,p} attn[n,q,m,l,p] * bilinear(value_l[n,:,m,c], loc[n,q,m,l,p])
@@ -121,6 +130,7 @@ MSDA_API int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_e
 /*
  * Fused Snipper snippet attention (one launch per transformer layer).
  *   value            (N,T2,S,M,D)       element strides value_stride_n / value_stride_t
+ *                                       [MSDA_FLAG_PRESUMMED: (N,slots,S,M,D), see msda_frame_sum]
  *   offsets          (N,T1,Lq,M,L,P,2)  raw sampling_offsets Linear output, in pixels
  *   logits           (N,T1,Lq,M,L,P)    raw attention_weights Linear output
  *                                       both dense per (n,t1,q) row; offsets_row_stride / logits_row_stride =
@@ -130,6 +140,11 @@ MSDA_API int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_e
  *   logits_bias      (M,L,P)   or NULL  epilogue pass over the projection output)
  *   reference_points (N,T1,Lq,L,2)      element strides ref_stride_n / ref_stride_t (0 allowed:
  *                                       the encoder expands one frame over T1)
+ *   value_mask       NULL, or the padding mask over value (N,T2,S,M*D) (layout: see Conventions): masked
+ *                                       elements are gathered as zero and receive no gradient -- the
+ *                                       reference's value.masked_fill(mask, 0) (ms_deform_attn.py:116-117)
+ *                                       without a pass over the value tensor.  Not with MSDA_FLAG_PRESUMMED
+ *                                       (msda_frame_sum / msda_frame_unsum apply the mask there).
  *   output           (N,T1,Lq,M*D)      contiguous
  * Per (n,t1,q,m): A = softmax_{l,p}(logits) / k,  loc = ref + offsets / (W_l,H_l),
  * out = sum over the k neighbour frames t2 of msda(value[:,t2], loc, A); neighbour frames are
@@ -148,13 +163,15 @@ MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shap
                          int64_t value_stride_n, int64_t value_stride_t,
                          int64_t ref_stride_n, int64_t ref_stride_t,
                          int64_t offsets_row_stride, int64_t logits_row_stride,
-                         const void *offsets_bias, const void *logits_bias, int dtype, void *stream);
+                         const void *offsets_bias, const void *logits_bias,
+                         const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
+                         int dtype, unsigned flags, void *stream);
 
 /*
- * grad_value (N,T2,S,M,D contiguous; zero-filled unless MSDA_FLAG_ACCUMULATE_VALUE),
- * grad_offsets like offsets, grad_logits like logits (same row strides).  The gradient w.r.t.
- * reference_points is sum_{m,p} grad_offsets * (W_l,H_l), the gradients of the biases are the sums of
- * grad_offsets / grad_logits over rows; both are left to the caller.
+ * grad_value (N,T2,S,M,D contiguous fp32 [MSDA_FLAG_PRESUMMED: (N,slots,S,M,D)]; zero-filled unless
+ * MSDA_FLAG_ACCUMULATE_VALUE), grad_offsets like offsets, grad_logits like logits (same row strides).
+ * The gradient w.r.t. reference_points is sum_{m,p} grad_offsets * (W_l,H_l), the gradients of the biases
+ * are the sums of grad_offsets / grad_logits over rows; both are left to the caller.
  */
 MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           const int64_t *level_start_index, const void *offsets, const void *logits,
@@ -166,8 +183,34 @@ MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_sha
                           int64_t value_stride_n, int64_t value_stride_t,
                           int64_t ref_stride_n, int64_t ref_stride_t,
                           int64_t offsets_row_stride, int64_t logits_row_stride,
-                          const void *offsets_bias, const void *logits_bias, int dtype, unsigned flags,
-                          void *stream);
+                          const void *offsets_bias, const void *logits_bias,
+                          const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
+                          int dtype, unsigned flags, void *stream);
+
+/*
+ * Neighbour-frame pre-summation.  The op is linear in `value` and the reference uses the same sampling
+ * locations and weights for every neighbour frame, so the sum over t2 (ms_deform_attn.py:225) can be taken
+ * BEFORE the gather:  slots = msda_snippet_num_slots(n_query_frames, n_frame);
+ *   slot j <  min(T1, n_frame):  frames max(j-1,0) .. min(j+1, n_frame-1);
+ *   slot j == min(T1, n_frame) (only if T1 > n_frame): all T2 frames (future query frames).
+ * msda_frame_sum    vsum (N,slots,S,C) [dtype]   = per-slot sums of mask ? 0 : value (N,T2,S,C)
+ * msda_frame_unsum  grad_value (N,T2,S,C) [dtype] = mask ? 0 : sum of the fp32 grad_vsum slots covering t2
+ * C = M*D (C % 4 == 0; bf16: C % 8 == 0).  Then call the snippet entries with MSDA_FLAG_PRESUMMED.
+ * msda_snippet_prefers_presum: 1 when the streaming pass costs less than the neighbour-frame gathers it
+ * removes (encoder-sized query sets), 0 for few queries (decoder) or a single frame.
+ */
+MSDA_API int msda_snippet_num_slots(int n_query_frames, int n_frame);
+MSDA_API int msda_snippet_prefers_presum(int n_src_frames, int n_query_frames, int n_frame, int spatial_size,
+                                         int num_levels, int num_query, int num_point);
+MSDA_API int msda_frame_sum(const void *value, const unsigned char *value_mask, void *vsum,
+                            int batch, int n_src_frames, int n_query_frames, int n_frame,
+                            int spatial_size, int row_elems,
+                            int64_t value_stride_n, int64_t value_stride_t,
+                            int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream);
+MSDA_API int msda_frame_unsum(const void *grad_vsum, const unsigned char *value_mask, void *grad_value,
+                              int batch, int n_src_frames, int n_query_frames, int n_frame,
+                              int spatial_size, int row_elems,
+                              int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import os
 
 from .build import LIB_PATH
 
-MSDA_ABI_VERSION = 2
+MSDA_ABI_VERSION = 3
 
 MSDA_OK = 0
 MSDA_ERR_INVALID_ARGUMENT = 1
@@ -24,12 +24,14 @@ MSDA_DTYPE_BF16 = 2
 
 MSDA_FLAG_DETERMINISTIC = 1
 MSDA_FLAG_ACCUMULATE_VALUE = 2
+MSDA_FLAG_PRESUMMED = 4
 
 # every symbol include/msda_b200.h declares
 EXPORTS = (
-    "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_set_tuning", "msda_forward",
+    "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_forward",
     "msda_backward", "msda_backward_workspace_bytes", "msda_masked_zero", "msda_snippet_forward",
-    "msda_snippet_backward",
+    "msda_snippet_backward", "msda_snippet_num_slots", "msda_snippet_prefers_presum", "msda_frame_sum",
+    "msda_frame_unsum",
 )
 
 _lib = None
@@ -59,8 +61,6 @@ def lib():
     L.msda_error_string.argtypes = [i32]
     L.msda_last_cuda_error.restype = i32
     L.msda_last_cuda_error.argtypes = []
-    L.msda_set_tuning.restype = i32
-    L.msda_set_tuning.argtypes = [ctypes.c_char_p, i32]
     L.msda_forward.restype = i32
     L.msda_forward.argtypes = [vp] * 6 + [i32] * 7 + [i64, i32, i32, vp]
     L.msda_backward.restype = i32
@@ -70,9 +70,17 @@ def lib():
     L.msda_masked_zero.restype = i32
     L.msda_masked_zero.argtypes = [vp, vp, i64, i32, vp]
     L.msda_snippet_forward.restype = i32
-    L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 6 + [vp, vp, i32, vp]
+    L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp]
     L.msda_snippet_backward.restype = i32
-    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, i32, u32, vp]
+    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp]
+    L.msda_snippet_num_slots.restype = i32
+    L.msda_snippet_num_slots.argtypes = [i32, i32]
+    L.msda_snippet_prefers_presum.restype = i32
+    L.msda_snippet_prefers_presum.argtypes = [i32] * 7
+    L.msda_frame_sum.restype = i32
+    L.msda_frame_sum.argtypes = [vp, vp, vp] + [i32] * 6 + [i64, i64, i64, i32, i32, vp]
+    L.msda_frame_unsum.restype = i32
+    L.msda_frame_unsum.argtypes = [vp, vp, vp] + [i32] * 6 + [i64, i32, i32, vp]
     if L.msda_abi_version() != MSDA_ABI_VERSION:
         raise RuntimeError("libmsda_b200.so ABI %d != binding ABI %d; rebuild" %
                            (L.msda_abi_version(), MSDA_ABI_VERSION))

@@ -7,11 +7,6 @@
 #include <stdint.h>
 #include <string.h>
 
-namespace msda {
-extern int g_pairs_d48;
-extern int g_snip_pairs_d48;
-}  // namespace msda
-
 namespace {
 
 thread_local int g_last_cuda_error = 0;
@@ -54,15 +49,6 @@ extern "C" {
 int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 
 int msda_last_cuda_error(void) { return g_last_cuda_error; }
-
-int msda_set_tuning(const char *key, int value)
-{
-    if (key == nullptr) return MSDA_ERR_INVALID_ARGUMENT;
-    const bool ok = (value == 8 || value == 16 || value == 32);
-    if (!strcmp(key, "pairs_d48") && ok) { msda::g_pairs_d48 = value; return MSDA_OK; }
-    if (!strcmp(key, "snip_pairs_d48") && ok) { msda::g_snip_pairs_d48 = value; return MSDA_OK; }
-    return MSDA_ERR_INVALID_ARGUMENT;
-}
 
 const char *msda_error_string(int status)
 {
@@ -205,19 +191,35 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
         (float *)grad_sampling_loc, (float *)grad_attn_weight, d, s));
 }
 
+static int check_mask(const unsigned char *mask, int64_t row_stride, int col_stride)
+{
+    if (mask == nullptr) return MSDA_OK;
+    if (row_stride < 0 || (col_stride != 0 && col_stride != 1)) return MSDA_ERR_INVALID_ARGUMENT;
+    // per-channel masks are read as 32-bit words
+    if (col_stride == 1 && ((reinterpret_cast<uintptr_t>(mask) & 3u) || (row_stride & 3))) return MSDA_ERR_INVALID_ARGUMENT;
+    return MSDA_OK;
+}
+
 static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n_query_frames,
                         int n_frame, int spatial_size, int num_heads, int channels, int num_levels,
                         int num_query, int num_point, int64_t value_stride_n, int64_t value_stride_t,
                         int64_t ref_stride_n, int64_t ref_stride_t, int64_t offsets_row_stride,
-                        int64_t logits_row_stride, const void *offsets_bias, const void *logits_bias, int dtype)
+                        int64_t logits_row_stride, const void *offsets_bias, const void *logits_bias,
+                        const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
+                        int dtype, unsigned flags)
 {
     if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
     if (batch < 0 || num_query < 0 || n_src_frames <= 0 || n_query_frames <= 0 || n_frame <= 0 ||
         n_frame > n_src_frames || spatial_size <= 0 || num_heads <= 0 || channels <= 0 ||
         num_levels <= 0 || num_point <= 0)
         return MSDA_ERR_INVALID_ARGUMENT;
+    const bool presummed = (flags & MSDA_FLAG_PRESUMMED) != 0;
+    if (presummed && value_mask != nullptr) return MSDA_ERR_INVALID_ARGUMENT;  // the mask belongs to msda_frame_sum / _unsum
+    int st = check_mask(value_mask, mask_row_stride, mask_col_stride);
+    if (st != MSDA_OK) return st;
+    const int frames = presummed ? msda::snippet_num_slots(n_query_frames, n_frame) : n_src_frames;
     if (value_stride_t == 0) value_stride_t = (int64_t)spatial_size * num_heads * channels;
-    if (value_stride_n == 0) value_stride_n = value_stride_t * n_src_frames;
+    if (value_stride_n == 0) value_stride_n = value_stride_t * frames;
     if (value_stride_n < 0 || value_stride_t < 0 || ref_stride_n < 0 || ref_stride_t < 0)
         return MSDA_ERR_INVALID_ARGUMENT;
     const int64_t mlp = (int64_t)num_heads * num_levels * num_point;
@@ -228,7 +230,8 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
     d = msda::SnippetDims{batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
-                          static_cast<const float *>(offsets_bias), static_cast<const float *>(logits_bias)};
+                          static_cast<const float *>(offsets_bias), static_cast<const float *>(logits_bias),
+                          presummed ? 1 : 0, value_mask, mask_row_stride, mask_col_stride};
     if (!msda::snippet_ok(d, dtype == MSDA_DTYPE_BF16 ? 2 : 4)) return MSDA_ERR_INVALID_ARGUMENT;
     return MSDA_OK;
 }
@@ -253,13 +256,16 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
                          int64_t value_stride_n, int64_t value_stride_t,
                          int64_t ref_stride_n, int64_t ref_stride_t,
                          int64_t offsets_row_stride, int64_t logits_row_stride,
-                         const void *offsets_bias, const void *logits_bias, int dtype, void *stream)
+                         const void *offsets_bias, const void *logits_bias,
+                         const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
+                         int dtype, unsigned flags, void *stream)
 {
+    if (flags & ~MSDA_FLAG_PRESUMMED) return MSDA_ERR_INVALID_ARGUMENT;
     msda::SnippetDims d;
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
-                          offsets_bias, logits_bias, dtype);
+                          offsets_bias, logits_bias, value_mask, mask_row_stride, mask_col_stride, dtype, flags);
     if (st != MSDA_OK) return st;
     if (batch == 0 || num_query == 0) return MSDA_OK;
     if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points || !output)
@@ -287,18 +293,23 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           int64_t value_stride_n, int64_t value_stride_t,
                           int64_t ref_stride_n, int64_t ref_stride_t,
                           int64_t offsets_row_stride, int64_t logits_row_stride,
-                          const void *offsets_bias, const void *logits_bias, int dtype, unsigned flags,
-                          void *stream)
+                          const void *offsets_bias, const void *logits_bias,
+                          const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
+                          int dtype, unsigned flags, void *stream)
 {
+    if (flags & ~(MSDA_FLAG_PRESUMMED | MSDA_FLAG_ACCUMULATE_VALUE | MSDA_FLAG_DETERMINISTIC)) return MSDA_ERR_INVALID_ARGUMENT;
+    // the deterministic mode of the fused layer is composed from msda_frame_sum + msda_backward(DETERMINISTIC)
+    // by the host side (snipper_b200/ops.py); this entry point itself always scatters with vector reductions
+    if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_INVALID_ARGUMENT;
     msda::SnippetDims d;
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
-                          offsets_bias, logits_bias, dtype);
+                          offsets_bias, logits_bias, value_mask, mask_row_stride, mask_col_stride, dtype, flags);
     if (st != MSDA_OK) return st;
-    if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_UNSUPPORTED_DTYPE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t value_elems = (size_t)batch * n_src_frames * spatial_size * num_heads * channels;
+    const int gframes = (flags & MSDA_FLAG_PRESUMMED) ? msda::snippet_num_slots(n_query_frames, n_frame) : n_src_frames;
+    const size_t value_elems = (size_t)batch * gframes * spatial_size * num_heads * channels;
     if (!(flags & MSDA_FLAG_ACCUMULATE_VALUE) && value_elems > 0) {
         if (!grad_value) return MSDA_ERR_INVALID_ARGUMENT;
         st = cuda_status(cudaMemsetAsync(grad_value, 0, sizeof(float) * value_elems, s));
@@ -321,6 +332,86 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
         (const float *)value, spatial_shapes, level_start_index, (const float *)offsets,
         (const float *)logits, (const float *)reference_points, (const float *)grad_output,
         (float *)grad_value, (float *)grad_offsets, (float *)grad_logits, d, s));
+}
+
+int msda_snippet_num_slots(int n_query_frames, int n_frame)
+{
+    if (n_query_frames <= 0 || n_frame <= 0) return 0;
+    return msda::snippet_num_slots(n_query_frames, n_frame);
+}
+
+int msda_snippet_prefers_presum(int n_src_frames, int n_query_frames, int n_frame, int spatial_size,
+                                int num_levels, int num_query, int num_point)
+{
+    if (n_src_frames <= 0 || n_query_frames <= 0 || n_frame <= 0 || n_frame > n_src_frames) return 0;
+    // (t1,t2) pairs the direct gather walks (reference ms_deform_attn.py:137-140,189,201)
+    int64_t pairs = 0;
+    for (int t1 = 0; t1 < n_query_frames; ++t1) {
+        if (t1 < n_frame) {
+            const int lo = t1 > 0 ? t1 - 1 : 0, hi = t1 + 1 < n_frame ? t1 + 1 : n_frame - 1;
+            pairs += hi - lo + 1;
+        } else {
+            pairs += n_src_frames;
+        }
+    }
+    // cells gathered by the neighbour-frame loop that the presummed gather does not touch (per head) ...
+    const int64_t saved = (pairs - n_query_frames) * (int64_t)num_query * num_levels * num_point * 4;
+    // ... against the cells the streaming pass reads and writes (forward; the backward mirrors it)
+    const int64_t slots = msda::snippet_num_slots(n_query_frames, n_frame);
+    const int64_t streamed = ((int64_t)n_src_frames + slots) * spatial_size;
+    return saved >= 4 * streamed ? 1 : 0;
+}
+
+static int frame_dims(msda::FrameDims &d, int batch, int n_src_frames, int n_query_frames, int n_frame,
+                      int spatial_size, int row_elems, int64_t value_stride_n, int64_t value_stride_t,
+                      const unsigned char *mask, int64_t mask_row_stride, int mask_col_stride, int dtype)
+{
+    if (dtype != MSDA_DTYPE_F32 && dtype != MSDA_DTYPE_BF16) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (batch < 0 || n_src_frames <= 0 || n_query_frames <= 0 || n_frame <= 0 || n_frame > n_src_frames ||
+        spatial_size <= 0 || row_elems <= 0)
+        return MSDA_ERR_INVALID_ARGUMENT;
+    int st = check_mask(mask, mask_row_stride, mask_col_stride);
+    if (st != MSDA_OK) return st;
+    if (value_stride_t == 0) value_stride_t = (int64_t)spatial_size * row_elems;
+    if (value_stride_n == 0) value_stride_n = value_stride_t * n_src_frames;
+    if (value_stride_n < 0 || value_stride_t < 0) return MSDA_ERR_INVALID_ARGUMENT;
+    d = msda::FrameDims{batch, n_src_frames, n_query_frames, n_frame, spatial_size, row_elems, value_stride_n,
+                        value_stride_t, mask ? mask_row_stride : 0, mask ? mask_col_stride : 0};
+    return MSDA_OK;
+}
+
+int msda_frame_sum(const void *value, const unsigned char *value_mask, void *vsum,
+                   int batch, int n_src_frames, int n_query_frames, int n_frame,
+                   int spatial_size, int row_elems, int64_t value_stride_n, int64_t value_stride_t,
+                   int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream)
+{
+    msda::FrameDims d;
+    int st = frame_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, row_elems, value_stride_n,
+                        value_stride_t, value_mask, mask_row_stride, mask_col_stride, dtype);
+    if (st != MSDA_OK) return st;
+    const int esize = dtype == MSDA_DTYPE_BF16 ? 2 : 4;
+    if (!msda::frame_dims_ok(d, esize)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (batch == 0) return MSDA_OK;
+    if (!value || !vsum || !aligned16(value) || !aligned16(vsum)) return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_frame_sum(value, value_mask, vsum, d, esize, static_cast<cudaStream_t>(stream)));
+}
+
+int msda_frame_unsum(const void *grad_vsum, const unsigned char *value_mask, void *grad_value,
+                     int batch, int n_src_frames, int n_query_frames, int n_frame,
+                     int spatial_size, int row_elems, int64_t mask_row_stride, int mask_col_stride,
+                     int dtype, void *stream)
+{
+    msda::FrameDims d;
+    int st = frame_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, row_elems, 0, 0,
+                        value_mask, mask_row_stride, mask_col_stride, dtype);
+    if (st != MSDA_OK) return st;
+    if (!msda::frame_dims_ok(d, 4)) return MSDA_ERR_INVALID_ARGUMENT;   // one thread per 4 fp32 channels
+    if (batch == 0) return MSDA_OK;
+    if (!grad_vsum || !grad_value || !aligned16(grad_vsum) || (reinterpret_cast<uintptr_t>(grad_value) & 7u))
+        return MSDA_ERR_INVALID_ARGUMENT;
+    if (dtype == MSDA_DTYPE_F32 && !aligned16(grad_value)) return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_frame_unsum(static_cast<const float *>(grad_vsum), value_mask, grad_value, d,
+                                                dtype == MSDA_DTYPE_BF16 ? 2 : 4, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -24,13 +24,19 @@ struct LevelTable {
     int start[kMaxLevels];
 };
 
+// A level whose slab [start, start + H*W) does not lie inside the S cells of a batch item is given an
+// empty extent, so every corner on it is invalid: inconsistent spatial_shapes / level_start_index (the
+// reference asserts (H*W).sum() == Len_in on the host, ms_deform_attn.py:112 -- a device sync per call)
+// can never turn into an out-of-bounds gather or reduction.
 __device__ __forceinline__ void load_level_table(LevelTable &t, const int64_t *__restrict__ shapes,
-                                                 const int64_t *__restrict__ lsi, int L)
+                                                 const int64_t *__restrict__ lsi, int L, int S)
 {
     for (int l = threadIdx.x; l < L; l += blockDim.x) {
-        t.H[l] = (int)shapes[2 * l];
-        t.W[l] = (int)shapes[2 * l + 1];
-        t.start[l] = (int)lsi[l];
+        const int64_t H = shapes[2 * l], W = shapes[2 * l + 1], start = lsi[l];
+        const bool ok = H >= 0 && W >= 0 && start >= 0 && H <= S && W <= S && start + H * W <= (int64_t)S;
+        t.H[l] = ok ? (int)H : 0;
+        t.W[l] = ok ? (int)W : 0;
+        t.start[l] = ok ? (int)start : 0;
     }
 }
 

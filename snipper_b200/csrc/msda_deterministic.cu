@@ -63,7 +63,7 @@ det_count_fill_kernel(const int64_t *__restrict__ shapes, const int64_t *__restr
                       CornerRec *__restrict__ records, int S, int M, int L, int P, int Lq, int64_t total_samples)
 {
     __shared__ LevelTable lv;
-    load_level_table(lv, shapes, lsi, L);
+    load_level_table(lv, shapes, lsi, L, S);
     __syncthreads();
     const int LP = L * P;
     for (int64_t si = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; si < total_samples;

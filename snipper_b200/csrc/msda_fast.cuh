@@ -22,6 +22,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "msda_common.cuh"
 
@@ -401,6 +402,15 @@ __device__ __forceinline__ int lane_chunk(int tid, int lane, int m)
 // Queries per CTA tile for D = 48.  The tuned default is 16; when that would leave the GPU with
 // fewer than ~3 CTAs per SM (decoder: Lq = 60) halve the tile so twice as many CTAs are in flight
 // -- those launches are latency-bound, not bandwidth-bound.
+// benchmark knob: tile length from the environment (8, 16 or 32; anything else = the tuned 16)
+inline int env_tile_pairs(const char *name)
+{
+    const char *e = getenv(name);
+    if (e == nullptr) return 16;
+    const int v = atoi(e);
+    return (v == 8 || v == 16 || v == 32) ? v : 16;
+}
+
 inline int pick_pairs_d48(int configured, int Lq, int M, int nz)
 {
     if (configured != 16) return configured;

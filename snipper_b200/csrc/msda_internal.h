@@ -24,6 +24,22 @@ struct SnippetDims {
     // optional biases of the two Linear layers, added here instead of in a GEMM epilogue kernel
     const float *off_bias;    // (M, L, P, 2) or nullptr
     const float *logit_bias;  // (M, L, P) or nullptr
+    // presummed: `value` (and grad_value) hold one frame per SLOT (msda_frames.cu) instead of one per
+    // source frame: (N, n_slots, S, M, D) with the strides above; each query frame gathers exactly one
+    int presummed;
+    // optional padding mask applied to the gathered value / the scattered grad_value (direct mode only):
+    // element (n,t,s,c) at mask[((n*T2+t)*S+s)*mask_row_stride + c*mask_col_stride], col stride 0 or 1
+    const uint8_t *mask;
+    int64_t mask_row_stride;
+    int mask_col_stride;
+};
+
+// neighbour-frame pre-summation (msda_frames.cu)
+struct FrameDims {
+    int N, T2, T1, n_frame, S, C;            // C = M * D
+    int64_t value_stride_n, value_stride_t;  // elements (frame_sum input only)
+    int64_t mask_row_stride;
+    int mask_col_stride;
 };
 
 // ---- per-call op (msda_percall.cu) ----
@@ -69,6 +85,14 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
 
 // ---- in-place masked zero-fill (msda_mask.cu) ----
 cudaError_t launch_masked_zero(void *data, const uint8_t *mask, int64_t n, int elem_bytes, cudaStream_t stream);
+
+// ---- neighbour-frame pre-summation (msda_frames.cu) ----
+int snippet_num_slots(int T1, int n_frame);
+bool frame_dims_ok(const FrameDims &d, int esize);
+cudaError_t launch_frame_sum(const void *value, const uint8_t *mask, void *vsum, const FrameDims &d, int esize,
+                             cudaStream_t stream);
+cudaError_t launch_frame_unsum(const float *grad_vsum, const uint8_t *mask, void *grad_value, const FrameDims &d,
+                               int out_esize, cudaStream_t stream);
 
 // ---- fused snippet op (msda_snippet.cu) ----
 bool snippet_ok(const SnippetDims &d);             // fp32

@@ -68,7 +68,7 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
     const int LP = a.L * a.P;
 
-    load_level_table(lv, shapes, lsi, a.L);
+    load_level_table(lv, shapes, lsi, a.L, a.S);
     __syncthreads();
 
     const int pl = tid / LANES;
@@ -138,7 +138,7 @@ msda_bwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS, nb = blockIdx.z;
     const int LP = a.L * a.P;
 
-    load_level_table(lv, shapes, lsi, a.L);
+    load_level_table(lv, shapes, lsi, a.L, a.S);
     __syncthreads();
 
     const int pl = tid / LANES;
@@ -234,7 +234,13 @@ bool fast_path_ok(const OpDims &d, int esize)
 
 bool fast_path_ok(const OpDims &d) { return fast_path_ok(d, 4); }
 
-int g_pairs_d48 = 16;  // queries per CTA tile for LANES == 12 (msda_set_tuning("pairs_d48", 8|16|32))
+// queries per CTA tile for LANES == 12: 16 unless MSDA_PAIRS_D48 = 8 | 16 | 32 is set in the environment
+// (benchmark knob; read once, results never depend on it)
+static int pairs_d48()
+{
+    static const int v = env_tile_pairs("MSDA_PAIRS_D48");
+    return v;
+}
 
 template <typename VT, int LANES, int PAIRS>
 static FastArgs make_fast_args(const OpDims &d)  // VT = lane type (float, __nv_bfloat16, bf16q)
@@ -304,7 +310,7 @@ static cudaError_t launch_bwd_fast(const typename Chunk<VT>::elem *value, const 
         case 4: return CALL(float, 4, 16);                            \
         case 8: return CALL(float, 8, 16);                            \
         case 12: {                                                    \
-            const int pairs_ = pick_pairs_d48(g_pairs_d48, d.Lq, d.M, d.N); \
+            const int pairs_ = pick_pairs_d48(pairs_d48(), d.Lq, d.M, d.N); \
             if (pairs_ == 8) return CALL(float, 12, 8);               \
             if (pairs_ == 32) return CALL(float, 12, 32);             \
             return CALL(float, 12, 16);                               \
@@ -393,10 +399,10 @@ __global__ void __launch_bounds__(256)
 msda_fwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const T *__restrict__ loc,
                         const T *__restrict__ attn, T *__restrict__ out,
-                        int M, int D, int L, int P, int Lq, int64_t total, int64_t value_batch_stride)
+                        int S, int M, int D, int L, int P, int Lq, int64_t total, int64_t value_batch_stride)
 {
     __shared__ LevelTable lv;
-    load_level_table(lv, shapes, lsi, L);
+    load_level_table(lv, shapes, lsi, L, S);
     __syncthreads();
     const int LP = L * P;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -436,7 +442,7 @@ msda_bwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__
                         int64_t value_batch_stride, bool scatter)
 {
     __shared__ LevelTable lv;
-    load_level_table(lv, shapes, lsi, L);
+    load_level_table(lv, shapes, lsi, L, S);
     __syncthreads();
     const int LP = L * P;
     const int lane = threadIdx.x & 31;
@@ -498,7 +504,7 @@ cudaError_t launch_forward_generic(const T *value, const int64_t *shapes, const 
     if (total == 0) return cudaSuccess;
     const int64_t blocks = (total + 255) / 256;
     const int grid = (int)(blocks < 148 * 64 ? blocks : 148 * 64);
-    msda_fwd_generic_kernel<T><<<grid, 256, 0, stream>>>(value, shapes, lsi, loc, attn, out, d.M, d.D,
+    msda_fwd_generic_kernel<T><<<grid, 256, 0, stream>>>(value, shapes, lsi, loc, attn, out, d.S, d.M, d.D,
                                                          d.L, d.P, d.Lq, total, d.value_batch_stride);
     return cudaGetLastError();
 }

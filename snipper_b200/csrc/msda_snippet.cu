@@ -22,6 +22,17 @@ namespace msda {
 
 constexpr int kSnippetMaxLP = 32;
 
+#ifndef MSDA_BWD_PRESUM_THREADS
+#define MSDA_BWD_PRESUM_THREADS 960   // resident threads per SM the presummed backward is compiled for (5 x 192)
+#endif
+
+// How phase 2 reaches `value` (a template constant: the three bodies share phase 1 and the epilogues)
+//   kDirect        gather every neighbour frame of value (N,T2,S,M,D)            -- few queries (decoder)
+//   kDirectMasked  same, with the padding mask applied to every gathered chunk / scattered reduction
+//   kPresummed     `value` holds the neighbour-frame SUMS, one slot per query frame (msda_frames.cu):
+//                  one gather per sample instead of |nb(t1)|                      -- encoder
+enum { kDirect = 0, kDirectMasked = 1, kPresummed = 2 };
+
 // grid = (M, query tiles, N*T1): a CTA owns PAIRS consecutive queries of ONE head of one
 // (batch item, query frame); neighbouring encoder queries gather overlapping cells (L1 hits).
 template <int LANES, int PAIRS_>
@@ -31,6 +42,8 @@ struct SnipCfg {
     static constexpr int SUBG = sub_group(LANES);
     static constexpr int SUBS = LANES / SUBG;
     static constexpr int BWD_MIN_BLOCKS = 768 / THREADS < 1 ? 1 : (768 / THREADS > 16 ? 16 : 768 / THREADS);  // <= 80 regs
+    // presummed backward: no neighbour-frame loop to keep in flight, so a tighter register budget costs nothing
+    static constexpr int BWD_MIN_BLOCKS_PRESUM = MSDA_BWD_PRESUM_THREADS / THREADS < 1 ? 1 : (MSDA_BWD_PRESUM_THREADS / THREADS > 16 ? 16 : MSDA_BWD_PRESUM_THREADS / THREADS);
     static_assert(LANES % 2 == 0 && THREADS % 32 == 0 && THREADS <= 1024, "lane groups must tile warps");
 };
 
@@ -38,7 +51,98 @@ struct SnipArgs {
     SnippetDims d;
     int cell_bytes;            // M * D * sizeof(VT)
     unsigned magic_LP, magic_P;
+    int n_local, n_slots;      // presummed: slot of query frame t1 = t1 < n_frame ? t1 : n_local
 };
+
+// ---- padding mask applied in the gather (kDirectMasked) ----
+// bit i set <=> channel i of the lane's chunk is masked (col stride 0: one byte per pixel)
+template <int N>
+__device__ __forceinline__ unsigned lane_mask_bits(const uint8_t *__restrict__ mp, int col_stride)
+{
+    if (col_stride == 0) return __ldg(mp) ? (1u << N) - 1u : 0u;
+    unsigned bits = 0u;
+#pragma unroll
+    for (int w = 0; w < N / 4; ++w) {
+        const unsigned mk = __ldg(reinterpret_cast<const unsigned *>(mp) + w);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if ((mk >> (8 * b)) & 0xffu) bits |= 1u << (4 * w + b);
+    }
+    return bits;
+}
+
+template <typename C>
+__device__ __forceinline__ C masked_load(const char *__restrict__ vp, unsigned bits)
+{
+    C v = C::load(vp);
+#pragma unroll
+    for (int i = 0; i < C::N; ++i)
+        if (bits & (1u << i)) v.x[i] = 0.f;
+    return v;
+}
+
+struct MaskView {
+    const uint8_t *p;      // mask element of (n, first gathered frame, cell 0, this lane's first channel)
+    int64_t row, frame;    // bytes between consecutive cells / frames
+    int col;
+};
+
+// forward, all neighbour frames, every gathered chunk masked (value.masked_fill(mask, 0), ms_deform_attn.py:116-117)
+template <typename VT>
+__device__ __forceinline__ void gather_fma_frames_masked(Chunk<VT> &acc, const SampleMeta mt, const float4 w,
+                                                         const char *__restrict__ pf, int64_t frame_bytes, int nf,
+                                                         int csb, const MaskView &mv)
+{
+    using C = Chunk<VT>;
+    const unsigned cm = mt.wm >> 28;
+    if (cm == 0u) return;
+    const int row = (int)(mt.wm & 0x0fffffffu);
+    const int64_t cell0 = mt.off / csb, wl = row / csb;   // exact: both are multiples of the cell stride
+    const char *a0 = pf + (ptrdiff_t)mt.off;
+    const uint8_t *m0 = mv.p + cell0 * mv.row;
+    for (int f = 0; f < nf; ++f, a0 += frame_bytes, m0 += mv.frame) {
+        if (cm & 1u) fma_chunk(acc, w.x, masked_load<C>(a0, lane_mask_bits<C::N>(m0, mv.col)));
+        if (cm & 2u) fma_chunk(acc, w.y, masked_load<C>(a0 + csb, lane_mask_bits<C::N>(m0 + mv.row, mv.col)));
+        if (cm & 4u) fma_chunk(acc, w.z, masked_load<C>(a0 + row, lane_mask_bits<C::N>(m0 + wl * mv.row, mv.col)));
+        if (cm & 8u) fma_chunk(acc, w.w, masked_load<C>(a0 + row + csb, lane_mask_bits<C::N>(m0 + (wl + 1) * mv.row, mv.col)));
+    }
+}
+
+// backward of one sample on one frame with the mask: masked channels of value read as zero and receive no gradient
+template <typename VT>
+__device__ __forceinline__ void gather_scatter_masked(const SampleMeta mt, const BwdWeights &b, const Chunk<VT> &g,
+                                                      const RedView<VT> &gr, const char *__restrict__ p0, char *gp0,
+                                                      int csb, const uint8_t *__restrict__ m0, int64_t mrow, int mcol,
+                                                      float &pa, float &px, float &py)
+{
+    using C = Chunk<VT>;
+    static_assert(C::N == 4, "backward lanes own four channels");
+    constexpr int GS = 4 / (int)sizeof(typename C::elem);
+    const unsigned cm = mt.wm >> 28;
+    if (cm == 0u) return;
+    const int row = (int)(mt.wm & 0x0fffffffu);
+    const int64_t cell0 = mt.off / csb, wl = row / csb;
+    const ptrdiff_t o[4] = {(ptrdiff_t)mt.off, (ptrdiff_t)mt.off + csb, (ptrdiff_t)mt.off + row, (ptrdiff_t)mt.off + row + csb};
+    const int64_t mc[4] = {cell0, cell0 + 1, cell0 + wl, cell0 + wl + 1};
+    const float aw[4] = {b.a0, b.a1, b.a2, b.a3};
+    float dk[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(cm & (1u << k))) continue;
+        const unsigned bits = lane_mask_bits<4>(m0 + mc[k] * mrow, mcol);
+        dk[k] = dot_chunk(g, masked_load<C>(p0 + o[k], bits));
+        if (bits != 0xfu) {
+            RedView<VT> gm = gr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (bits & (1u << i)) gm.x[i] = 0.f;
+            gm.red(gp0 + GS * o[k], aw[k]);
+        }
+    }
+    pa = fmaf(b.w0, dk[0], fmaf(b.w1, dk[1], fmaf(b.w2, dk[2], fmaf(b.w3, dk[3], pa))));
+    px = fmaf(b.hy, dk[1] - dk[0], fmaf(b.ly, dk[3] - dk[2], px));
+    py = fmaf(b.hx, dk[2] - dk[0], fmaf(b.lx, dk[3] - dk[1], py));
+}
 
 __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo, int &hi)
 {
@@ -116,7 +220,7 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es
 // until it is used up (56 registers + spills at a 6-CTA floor, 64 at 5, 80 at 4) and the kernel gets
 // SLOWER -- left alone it needs 40 registers, 8 CTAs per SM fit, and the gather is 10-13 % faster
 // (profiles/r01_run21_*): this kernel wants warps in flight, not loads per warp.
-template <typename VT, int LANES, int PAIRS, int CSB>
+template <typename VT, int LANES, int PAIRS, int CSB, int MODE>
 __global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS)
 msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
@@ -142,7 +246,7 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const int nf = hi - lo + 1;
     const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;  // first query row of this (n, t1)
 
-    load_level_table(lv, shapes, lsi, d.L);
+    load_level_table(lv, shapes, lsi, d.L, d.S);
     __syncthreads();
     snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits, ref,
                                             1.f / (float)nf);
@@ -153,23 +257,40 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     if (q0 + pl >= d.Lq) return;
     const int chunk = lane_chunk<VT, LANES>(tid, lane, m);
     const size_t pair = (qbase + q0 + pl) * d.M + m;
-    const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
+    // first frame this query frame gathers from: its slot (presummed) or its first neighbour frame
+    const int first = MODE == kPresummed ? (t1 < d.n_frame ? t1 : a.n_local) : lo;
+    const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + first * d.value_stride_t) +
                      (size_t)(m * LANES + chunk) * C::BYTES;
     const int64_t fstride = d.value_stride_t * (int64_t)sizeof(ET);  // bytes between frames
+    MaskView mv{nullptr, 0, 0, 0};
+    if (MODE == kDirectMasked) {
+        mv.row = d.mask_row_stride;
+        mv.frame = (int64_t)d.S * d.mask_row_stride;
+        mv.col = d.mask_col_stride;
+        mv.p = d.mask + ((int64_t)n * d.T2 + lo) * mv.frame + (int64_t)((m * LANES + chunk) * C::N) * mv.col;
+    }
     const float4 *rr = rec + pl * (LP + 1);
     C acc = zero_chunk<C>();
     for (int l = 0; l < d.L; ++l) {
         const unsigned row = (unsigned)(lv.W[l] * a.cell_bytes);
         for (int p = 0; p < d.P; ++p) {
             const float4 r = rr[l * d.P + p];
-            gather_fma_frames<VT, CSB>(acc, record_meta(r, row), record_weights(r), pf, fstride, nf, a.cell_bytes);
+            if (MODE == kPresummed)
+                gather_fma<VT, CSB>(acc, record_meta(r, row), record_weights(r), pf, a.cell_bytes);
+            else if (MODE == kDirect)
+                gather_fma_frames<VT, CSB>(acc, record_meta(r, row), record_weights(r), pf, fstride, nf, a.cell_bytes);
+            else
+                gather_fma_frames_masked<VT>(acc, record_meta(r, row), record_weights(r), pf, fstride, nf,
+                                             a.cell_bytes, mv);
         }
     }
     acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
 }
 
-template <typename VT, int LANES, int PAIRS, int CSB>
-__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS, SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS)
+template <typename VT, int LANES, int PAIRS, int CSB, int MODE>
+__global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS,
+                                  MODE == kPresummed ? SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS_PRESUM
+                                                     : SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS)
 msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
                         const float *__restrict__ logits, const float *__restrict__ ref,
@@ -198,7 +319,7 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const int nf = hi - lo + 1;
     const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;
 
-    load_level_table(lv, shapes, lsi, d.L);
+    load_level_table(lv, shapes, lsi, d.L, d.S);
     __syncthreads();
     snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(frac, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits, ref,
                                             1.f / (float)nf);
@@ -211,12 +332,18 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
         const int chunk = lane_chunk<VT, LANES>(tid, lane, m);
         const bool live = q0 + pl < d.Lq;
         const size_t pair = (qbase + q0 + pl) * d.M + m;
-        const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
+        const int first = MODE == kPresummed ? (t1 < d.n_frame ? t1 : a.n_local) : lo;
+        const int gframes = MODE == kPresummed ? a.n_slots : d.T2;  // frames per batch item of grad_value
+        const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + first * d.value_stride_t) +
                          (size_t)(m * LANES + chunk) * C::BYTES;
-        // grad_value is a dense fp32 (N,T2,S,M,D) buffer: GS x the value byte offsets
+        // grad_value is a dense fp32 (N,T2 | slots,S,M,D) buffer: GS x the value byte offsets
         char *gpf = reinterpret_cast<char *>(grad_value) +
-                    (((size_t)n * d.T2 + lo) * d.S * a.cell_bytes + (size_t)m * LANES * C::BYTES) * GS +
+                    (((size_t)n * gframes + first) * d.S * a.cell_bytes + (size_t)m * LANES * C::BYTES) * GS +
                     RedView<VT>::lane_offset(chunk);
+        const int64_t mframe = (int64_t)d.S * d.mask_row_stride;
+        const uint8_t *mpf = MODE == kDirectMasked
+                                 ? d.mask + ((int64_t)n * d.T2 + lo) * mframe + (int64_t)((m * LANES + chunk) * C::N) * d.mask_col_stride
+                                 : nullptr;
         C g = zero_chunk<C>();
         if (live) g = C::load(reinterpret_cast<const char *>(grad_out) + (pair * LANES + chunk) * C::BYTES);
         const RedView<VT> gr = RedView<VT>::make(g);
@@ -233,8 +360,17 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
             char *gp0 = gpf;
             // (the backward, unlike the forward, prefers loads in flight over occupancy: not unrolling
             //  this loop -- 64 registers, 5 CTAs per SM -- measured 4-7 % slower, profiles/r01_run24_*)
-            for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
+            if (MODE == kPresummed) {
                 gather_scatter<VT, CSB, true>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
+            } else if (MODE == kDirect) {
+                for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
+                    gather_scatter<VT, CSB, true>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
+            } else {
+                const uint8_t *mp = mpf;
+                for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride, mp += mframe)
+                    gather_scatter_masked<VT>(mt, bw, g, gr, p0, gp0, a.cell_bytes, mp, d.mask_row_stride,
+                                              d.mask_col_stride, pa, px, py);
+            }
             subgroup_sum3<Cfg::SUBG>(pa, px, py);
             // zs/es alias `part`: all phase-1 reads finished at the barrier that ends phase 1
             if ((lane & (Cfg::SUBG - 1)) == 0) {
@@ -291,7 +427,13 @@ bool snippet_ok(const SnippetDims &d, int esize)
 
 bool snippet_ok(const SnippetDims &d) { return snippet_ok(d, 4); }
 
-int g_snip_pairs_d48 = 16;  // msda_set_tuning("snip_pairs_d48", 8|16|32)
+// queries per CTA tile for D = 48: 16 unless MSDA_SNIP_PAIRS_D48 = 8 | 16 | 32 is set in the environment
+// (benchmark knob; read once, results never depend on it)
+int snip_pairs_d48()
+{
+    static const int v = env_tile_pairs("MSDA_SNIP_PAIRS_D48");
+    return v;
+}
 
 template <typename VT>
 static SnipArgs make_snip_args(const SnippetDims &d)
@@ -301,8 +443,12 @@ static SnipArgs make_snip_args(const SnippetDims &d)
     a.cell_bytes = d.M * d.D * (int)sizeof(typename Chunk<VT>::elem);
     a.magic_LP = fast_magic(d.L * d.P);
     a.magic_P = fast_magic(d.P);
+    a.n_local = d.T1 < d.n_frame ? d.T1 : d.n_frame;
+    a.n_slots = snippet_num_slots(d.T1, d.n_frame);
     return a;
 }
+
+static int snip_mode(const SnippetDims &d) { return d.presummed ? kPresummed : (d.mask ? kDirectMasked : kDirect); }
 
 // Snipper's cell stride (M*D = 384 elements) as an immediate offset
 template <typename VT, int LANES>
@@ -318,16 +464,25 @@ static cudaError_t launch_snip_fwd(const typename Chunk<VT>::elem *value, const 
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + 2 * sizeof(float) * Cfg::PAIRS * d.L * d.P;
     constexpr int C = snip_csb<VT, LANES>();
-    if (C != 0 && d.M * d.D == 384)
-        msda_snippet_fwd_kernel<VT, LANES, PAIRS, C><<<grid, Cfg::THREADS, smem, stream>>>(
-            value, shapes, lsi, offsets, logits, ref, out, a);
-    else
-        msda_snippet_fwd_kernel<VT, LANES, PAIRS, 0><<<grid, Cfg::THREADS, smem, stream>>>(
-            value, shapes, lsi, offsets, logits, ref, out, a);
+    const bool imm = C != 0 && d.M * d.D == 384;
+#define MSDA_LAUNCH_FWD(CSB_, MODE_)                                                                   \
+    msda_snippet_fwd_kernel<VT, LANES, PAIRS, CSB_, MODE_><<<grid, Cfg::THREADS, smem, stream>>>(     \
+        value, shapes, lsi, offsets, logits, ref, out, a)
+    switch (snip_mode(d)) {
+        case kPresummed:
+            if (imm) MSDA_LAUNCH_FWD(C, kPresummed); else MSDA_LAUNCH_FWD(0, kPresummed);
+            break;
+        case kDirectMasked:   // runtime cell stride only: the masked gather is the few-queries path
+            MSDA_LAUNCH_FWD(0, kDirectMasked);
+            break;
+        default:
+            if (imm) MSDA_LAUNCH_FWD(C, kDirect); else MSDA_LAUNCH_FWD(0, kDirect);
+    }
+#undef MSDA_LAUNCH_FWD
     return cudaGetLastError();
 }
 
-template <typename VT, int LANES, int PAIRS, int CSB>
+template <typename VT, int LANES, int PAIRS, int CSB, int MODE>
 static cudaError_t launch_snip_bwd_impl(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
                                         const float *offsets, const float *logits, const float *ref,
                                         const typename Chunk<VT>::elem *grad_out, float *grad_value, float *grad_offsets,
@@ -338,8 +493,9 @@ static cudaError_t launch_snip_bwd_impl(const typename Chunk<VT>::elem *value, c
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
     const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + sizeof(float) * 3 * Cfg::SUBS * Cfg::PAIRS * d.L * d.P;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB><<<grid, Cfg::THREADS, smem, stream>>>(
+        cudaFuncSetAttribute(msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB, MODE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    msda_snippet_bwd_kernel<VT, LANES, PAIRS, CSB, MODE><<<grid, Cfg::THREADS, smem, stream>>>(
         value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, a);
     return cudaGetLastError();
 }
@@ -351,11 +507,16 @@ static cudaError_t launch_snip_bwd(const typename Chunk<VT>::elem *value, const 
                                    float *grad_logits, const SnippetDims &d, cudaStream_t stream)
 {
     constexpr int C = snip_csb<VT, LANES>();
-    if (C != 0 && d.M * d.D == 384)
-        return launch_snip_bwd_impl<VT, LANES, PAIRS, C>(value, shapes, lsi, offsets, logits, ref, grad_out,
-                                                         grad_value, grad_offsets, grad_logits, d, stream);
-    return launch_snip_bwd_impl<VT, LANES, PAIRS, 0>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value,
-                                                     grad_offsets, grad_logits, d, stream);
+    const bool imm = C != 0 && d.M * d.D == 384;
+#define MSDA_LAUNCH_BWD(CSB_, MODE_)                                                                             \
+    launch_snip_bwd_impl<VT, LANES, PAIRS, CSB_, MODE_>(value, shapes, lsi, offsets, logits, ref, grad_out,     \
+                                                        grad_value, grad_offsets, grad_logits, d, stream)
+    switch (snip_mode(d)) {
+        case kPresummed: return imm ? MSDA_LAUNCH_BWD(C, kPresummed) : MSDA_LAUNCH_BWD(0, kPresummed);
+        case kDirectMasked: return MSDA_LAUNCH_BWD(0, kDirectMasked);
+        default: return imm ? MSDA_LAUNCH_BWD(C, kDirect) : MSDA_LAUNCH_BWD(0, kDirect);
+    }
+#undef MSDA_LAUNCH_BWD
 }
 
 #define MSDA_DISPATCH_LANES(D, CALL)                                  \
@@ -363,7 +524,7 @@ static cudaError_t launch_snip_bwd(const typename Chunk<VT>::elem *value, const 
         case 4: return CALL(float, 4, 16);                            \
         case 8: return CALL(float, 8, 16);                            \
         case 12: {                                                    \
-            const int pairs_ = pick_pairs_d48(g_snip_pairs_d48, d.Lq, d.M, d.N * d.T1); \
+            const int pairs_ = pick_pairs_d48(snip_pairs_d48(), d.Lq, d.M, d.N * d.T1); \
             if (pairs_ == 8) return CALL(float, 12, 8);               \
             if (pairs_ == 32) return CALL(float, 12, 32);             \
             return CALL(float, 12, 16);                               \

@@ -38,6 +38,62 @@ def neighbour_frames(t1, n_frame, n_src_frames):
     return list(range(n_src_frames))
 
 
+class _LazyList(list):
+    """A list whose elements are produced on first access (len, indexing, iteration)."""
+
+    def __init__(self, owner, which):
+        super().__init__()
+        self._owner, self._which, self._ready = owner, which, False
+
+    def _fill(self):
+        if not self._ready:
+            self._ready = True
+            super().extend(self._owner.materialise()[self._which])
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def __getitem__(self, i):
+        self._fill()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __repr__(self):
+        self._fill()
+        return super().__repr__()
+
+
+class LazyVis:
+    """The decoder's ``attention_vis`` payload (reference :228-233: per query frame, sampling locations
+    (N,Lq,M,L,P,k,2) and attention weights (N,Lq,M,L,P,k)).  Only the reference's visualiser reads them, so
+    the fused path hands out two lists that compute their tensors when first touched instead of running
+    ~20 small launches in every decoder layer of every forward.  The inputs are kept by reference: read the
+    lists before the buffers are reused (e.g. before the next CUDA-graph replay)."""
+
+    def __init__(self, module, proj, off_bias, logit_bias, ref, spatial_shapes, T2):
+        self.args = (module, proj, off_bias, logit_bias, ref, spatial_shapes, T2)
+        self.out = None
+
+    def lists(self):
+        return _LazyList(self, 0), _LazyList(self, 1)
+
+    def materialise(self):
+        if self.out is None:
+            module, proj, off_bias, logit_bias, ref, spatial_shapes, T2 = self.args
+            N, T1, Lq, _ = proj.shape
+            M, L, P = module.n_heads, module.n_levels, module.n_points
+            n_off = 2 * M * L * P
+            offsets = (proj[..., :n_off] + off_bias).view(N, T1, Lq, M, L, P, 2)
+            logits = (proj[..., n_off:] + logit_bias).view(N, T1, Lq, M, L, P)
+            self.out = module._vis_fused(offsets, logits, ref, spatial_shapes, T2)
+            self.args = None
+        return self.out
+
+
 class MSDeformAttn(nn.Module):
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, n_frame=4,
                  mode="encoder", use_pytroch_deform=False, attention_vis=False):
@@ -55,6 +111,7 @@ class MSDeformAttn(nn.Module):
         self.mode = mode
         self.attention_vis = attention_vis
         self.fused = True
+        self._proj_cache = None
 
         offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.sampling_offsets = nn.ModuleList([offsets for _ in range(n_frame)])
@@ -90,55 +147,74 @@ class MSDeformAttn(nn.Module):
         so, aw = self.sampling_offsets, self.attention_weights
         return all(m is so[0] for m in so) and all(m is aw[0] for m in aw)
 
-    def _can_fuse(self, value):
-        if ops.is_deterministic() and torch.is_grad_enabled():
-            return False  # the deterministic grad_value path lives in the per-call backward
+    def _can_fuse(self, value, spatial_size=0, batch_frames=0):
+        """Every condition the fused C entry points check (so anything else degrades to the per-call loop
+        instead of raising): aliased frame slots, supported head size / sample count, 28-bit cell offsets,
+        gridDim.z, and a float32 deterministic mode."""
+        if ops.is_deterministic() and torch.is_grad_enabled() and value.dtype != torch.float32:
+            return False  # the deterministic grad_value path is float32 only
         return (self.fused and self._slots_aliased() and value.is_cuda and
                 ops.snippet_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
-                                      self.n_points, value.dtype))
+                                      self.n_points, value.dtype, spatial_size, batch_frames))
+
+    def _stacked_projection(self):
+        """[sampling_offsets | attention_weights] weights as ONE (3*M*L*P, C) matrix and the two biases in
+        fp32.  Rebuilt only when a parameter changed (inference: once); under autograd it is a plain cat
+        so the gradient reaches both Linear layers."""
+        so, aw = self.sampling_offsets[0], self.attention_weights[0]
+        if torch.is_grad_enabled() and (so.weight.requires_grad or aw.weight.requires_grad):
+            return torch.cat((so.weight, aw.weight), 0), so.bias.float(), aw.bias.float()
+        key = (so.weight.data_ptr(), so.weight._version, aw.weight.data_ptr(), aw.weight._version,
+               so.bias.data_ptr(), so.bias._version, aw.bias.data_ptr(), aw.bias._version, so.weight.dtype)
+        if self._proj_cache is None or self._proj_cache[0] != key:
+            with torch.no_grad():
+                self._proj_cache = (key, torch.cat((so.weight, aw.weight), 0).contiguous(),
+                                    so.bias.detach().float().contiguous(), aw.bias.detach().float().contiguous())
+        return self._proj_cache[1:]
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
                 input_level_start_index, input_padding_mask=None):
         """query (N,T1,Lq,C); reference_points (N,T1,Lq,L,2) in [0,1]; input_flatten (N,T2,S,C);
         input_spatial_shapes (L,2) int64; input_level_start_index (L,) int64;
-        input_padding_mask (N,T2,S,C) bool, True = padding.  Returns (N,T1,Lq,C), plus
-        ``(sampling_locations per t1, attention_weights per t1)`` when ``attention_vis``."""
+        input_padding_mask (N,T2,S,C) bool, True = padding -- also accepted: a channel-expanded view or a
+        per-pixel (N,T2,S[,1]) mask, which the kernels then read as one byte per pixel.
+        Returns (N,T1,Lq,C), plus ``(sampling_locations per t1, attention_weights per t1)`` when
+        ``attention_vis``."""
         N, T1, Lq, _ = query.shape
         _, T2, S, _ = input_flatten.shape
         M, L, P = self.n_heads, self.n_levels, self.n_points
+        if input_spatial_shapes.shape[0] != L or input_level_start_index.numel() != L:
+            raise RuntimeError("input_spatial_shapes must be (n_levels, 2) and input_level_start_index (n_levels,)")
 
         value = self.value_proj(input_flatten)
-        value_mask = None
-        if input_padding_mask is not None:
-            if self._can_fuse(value) and ops.masked_zero_supported(value, input_padding_mask):
-                # in place on the projection's fresh output: reads the mask, writes only padded elements
-                # (the reference's masked_fill re-writes the whole tensor, :116-117); the fused op's
-                # backward zeroes the same elements of grad_value
-                value = ops.MaskedValue.apply(value, input_padding_mask)
-                value_mask = input_padding_mask
-            else:
-                value = value.masked_fill(input_padding_mask, 0.0)
-        value = value.view(N, T2, S, M, self.d_model // M)
 
-        if self._can_fuse(value):
+        if self._can_fuse(value, S, N * T1):
             # ONE GEMM for both per-query projections (the reference runs the two Linear layers once per
             # (t1,t2) pair, :143-145,162-163): the weights are stacked [sampling_offsets | attention_weights],
             # the biases are added inside the kernel (no GEMM epilogue pass over the projection output), and
-            # the kernel reads its offsets / logits as column blocks of the one output.
+            # the kernel reads its offsets / logits as column blocks of the one output.  The padding mask
+            # (:116-117) is applied inside the kernels as well -- value is never re-written.
             # value may be bf16 (autocast): the kernels gather bf16 and keep every location / weight
             # computation in fp32, so the projection and the reference points go in as fp32.
-            so, aw = self.sampling_offsets[0], self.attention_weights[0]
-            proj = F.linear(query, torch.cat((so.weight, aw.weight), 0)).float()
-            out = torch.ops.snipper_b200.snippet_forward_packed(
-                value, input_spatial_shapes, input_level_start_index, proj, so.bias, aw.bias,
-                reference_points.float(), self.n_frame, value_mask)
+            weight, off_bias, logit_bias = self._stacked_projection()
+            proj = F.linear(query, weight)
+            if proj.dtype != torch.float32:
+                proj = proj.float()
+            ref = reference_points if reference_points.dtype == torch.float32 else reference_points.float()
+            out = ops.snippet_attention(value.view(N, T2, S, M, self.d_model // M), input_padding_mask,
+                                        input_spatial_shapes, input_level_start_index, proj, off_bias, logit_bias,
+                                        ref, self.n_frame)
             vis = None
             if self.attention_vis:
-                n_off = so.weight.shape[0]
-                offsets = (proj[..., :n_off] + so.bias).view(N, T1, Lq, M, L, P, 2)
-                logits = (proj[..., n_off:] + aw.bias).view(N, T1, Lq, M, L, P)
-                vis = self._vis_fused(offsets, logits, reference_points, input_spatial_shapes, T2)
+                vis = LazyVis(self, proj.detach(), off_bias.detach(), logit_bias.detach(), ref.detach(),
+                              input_spatial_shapes, T2).lists()
         else:
+            if input_padding_mask is not None:
+                mask = input_padding_mask
+                if mask.dim() == 3:
+                    mask = mask.unsqueeze(-1)
+                value = value.masked_fill(mask, 0.0)
+            value = value.view(N, T2, S, M, self.d_model // M)
             out, vis = self._forward_per_call(query, reference_points, value, input_spatial_shapes,
                                               input_level_start_index)
         out = self.output_proj(out)

@@ -242,32 +242,20 @@ def masked_zero_supported(data: Tensor, mask: Tensor) -> bool:
             mask.is_contiguous() and mask.data_ptr() % 16 == 0)
 
 
-class MaskedValue(torch.autograd.Function):
-    """``value.masked_fill(mask, 0)`` done IN PLACE on the freshly produced projection output.
-
-    The backward is the identity ON PURPOSE: the only consumer of the result must be
-    ``snippet_forward(..., value_mask=mask)``, whose backward zeroes the masked elements of the
-    grad_value buffer it has just produced (same kernel, in place, no extra pass over the tensor).
-    Used only by the fused path of :class:`snipper_b200.modules.MSDeformAttn`."""
-
-    @staticmethod
-    def forward(ctx, value, mask):
-        torch.ops.snipper_b200.masked_zero_(value, mask)
-        ctx.mark_dirty(value)
-        return value
-
-    @staticmethod
-    def backward(ctx, grad):
-        return grad, None
-
-
 # ------------------------------------------------------------------------------------------
 # fused snippet op
 # ------------------------------------------------------------------------------------------
-def snippet_supported(n_heads: int, d_head: int, n_levels: int, n_points: int, dtype) -> bool:
-    """Shapes the fused kernels cover (include/msda_b200.h, msda_snippet_forward)."""
+def snippet_supported(n_heads: int, d_head: int, n_levels: int, n_points: int, dtype,
+                      spatial_size: int = 0, batch_frames: int = 0) -> bool:
+    """Shapes the fused kernels cover -- every constraint the C ABI enforces for the packed call
+    (include/msda_b200.h msda_snippet_forward; msda_snippet.cu snippet_ok), so that a caller can fall back
+    to the per-call loop instead of getting MSDA_ERR_INVALID_ARGUMENT."""
+    esize = 2 if dtype == torch.bfloat16 else 4
     return (dtype in (torch.float32, torch.bfloat16) and d_head % 16 == 0 and d_head <= 128 and
-            n_levels * n_points <= 32 and n_levels <= 64)
+            n_levels * n_points <= 32 and n_levels <= 64 and
+            (n_heads * n_levels * n_points) % 2 == 0 and                     # float2 loads of a packed projection row
+            spatial_size * n_heads * d_head * esize < (1 << 28) and          # cell byte offsets are 28-bit
+            batch_frames <= 65535)                                           # gridDim.z
 
 
 def _check_snippet(value, spatial_shapes, level_start_index, offsets, logits, ref, n_frame):
@@ -315,10 +303,8 @@ def _ref_strides(ref):
 
 @torch.library.custom_op("snipper_b200::snippet_forward", mutates_args=())
 def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
-                    offsets: Tensor, logits: Tensor, reference_points: Tensor, n_frame: int,
-                    value_mask: Optional[Tensor] = None) -> Tensor:
-    """``value_mask`` (bool, value's shape, contiguous) is not read here -- ``value`` must already be zero
-    where it is set (``MaskedValue``); it is carried to the backward, which zeroes those elements of grad_value."""
+                    offsets: Tensor, logits: Tensor, reference_points: Tensor, n_frame: int) -> Tensor:
+    """Fused layer attention on separate offsets / logits tensors, neighbour frames gathered directly."""
     N, T2, T1, S, M, D, L, Lq, P = _check_snippet(value, spatial_shapes, level_start_index, offsets,
                                                   logits, reference_points, n_frame)
     sn, st = _value_strides5(value)
@@ -328,14 +314,14 @@ def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Te
         status = capi.lib().msda_snippet_forward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), out.data_ptr(),
-            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None,
-            _DTYPES[value.dtype], _stream(value.device))
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, 0, 0,
+            _DTYPES[value.dtype], 0, _stream(value.device))
     capi.check(status, "msda_snippet_forward")
     return out
 
 
 @snippet_forward.register_fake
-def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame, value_mask=None):
+def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame):
     N, T2, S, M, D = value.shape
     return value.new_empty((N, offsets.shape[1], offsets.shape[2], M * D))
 
@@ -343,7 +329,7 @@ def _(value, spatial_shapes, level_start_index, offsets, logits, reference_point
 @torch.library.custom_op("snipper_b200::snippet_backward", mutates_args=())
 def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor,
                      offsets: Tensor, logits: Tensor, reference_points: Tensor, grad_output: Tensor,
-                     n_frame: int, value_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+                     n_frame: int) -> Tuple[Tensor, Tensor, Tensor]:
     N, T2, T1, S, M, D, L, Lq, P = _check_snippet(value, spatial_shapes, level_start_index, offsets,
                                                   logits, reference_points, n_frame)
     _require_cuda(grad_output, "grad_output")
@@ -358,86 +344,104 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(),
-            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None,
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, 0, 0,
             _DTYPES[value.dtype], 0, _stream(value.device))
     capi.check(status, "msda_snippet_backward")
-    _mask_grad_value(grad_value, value_mask, value.device)
     if value.dtype != torch.float32:
         grad_value = grad_value.to(value.dtype)
     return grad_value, grad_offsets, grad_logits
 
 
-def _mask_grad_value(grad_value, value_mask, device):
-    if value_mask is not None:
-        # d(masked_fill)/d(value) : no gradient reaches the masked elements (fresh buffer, in place)
-        if value_mask.dtype != torch.bool or value_mask.numel() != grad_value.numel() or not value_mask.is_contiguous():
-            raise RuntimeError("value_mask must be a contiguous bool tensor with value's number of elements")
-        with torch.cuda.device(device), _Launch("masked_zero", (grad_value.numel(),), device):
-            status = capi.lib().msda_masked_zero(grad_value.data_ptr(), value_mask.data_ptr(), grad_value.numel(),
-                                                 capi.MSDA_DTYPE_F32, _stream(device))
-        capi.check(status, "msda_masked_zero")
-
-
 @snippet_backward.register_fake
-def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, grad_output, n_frame, value_mask=None):
+def _(value, spatial_shapes, level_start_index, offsets, logits, reference_points, grad_output, n_frame):
     return (value.new_empty(value.shape), torch.empty_like(offsets), torch.empty_like(logits))
 
 
 def _snippet_setup_context(ctx, inputs, output):
-    value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame, value_mask = inputs
+    value, spatial_shapes, level_start_index, offsets, logits, reference_points, n_frame = inputs
     ctx.n_frame = n_frame
-    ctx.has_mask = value_mask is not None
-    if ctx.has_mask:
-        ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points, value_mask)
-    else:
-        ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
+    ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
 
 
 def _snippet_backward_formula(ctx, grad_output):
-    if ctx.has_mask:
-        value, spatial_shapes, level_start_index, offsets, logits, ref, value_mask = ctx.saved_tensors
-    else:
-        value, spatial_shapes, level_start_index, offsets, logits, ref = ctx.saved_tensors
-        value_mask = None
+    value, spatial_shapes, level_start_index, offsets, logits, ref = ctx.saved_tensors
     gv, goff, glog = torch.ops.snipper_b200.snippet_backward(
-        value, spatial_shapes, level_start_index, offsets, logits, ref, grad_output.contiguous(), ctx.n_frame,
-        value_mask)
+        value, spatial_shapes, level_start_index, offsets, logits, ref, grad_output.contiguous(), ctx.n_frame)
     gref = None
     if ctx.needs_input_grad[5]:
         # loc = ref + off/(W,H)  =>  dL/dref = sum_{m,p} dL/dloc = sum_{m,p} dL/doff * (W,H)
         wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
         gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
-    return gv, None, None, goff, glog, gref, None, None
+    return gv, None, None, goff, glog, gref, None
 
 
 snippet_forward.register_autograd(_snippet_backward_formula, setup_context=_snippet_setup_context)
 
 
 # ------------------------------------------------------------------------------------------
-# fused snippet op, packed projection: offsets and logits are column blocks of ONE GEMM output and
-# the two Linear biases are added in-kernel (no second GEMM over the queries, no epilogue passes)
+# fused layer attention on the packed projection: offsets and logits are column blocks of ONE GEMM
+# output, the two Linear biases are added in-kernel, the padding mask is applied inside the kernels
+# (no pass over the value tensor) and, for encoder-sized query sets, the neighbour frames are summed
+# BEFORE the gather (msda_frame_sum: the op is linear in value) so every sample is gathered once
 # ------------------------------------------------------------------------------------------
-def _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref, n_frame):
+def mask_layout(mask: Optional[Tensor], N: int, T2: int, S: int, C: int):
+    """Padding mask over value (N,T2,S,C) -> (tensor to keep alive, row stride, col stride) for the C ABI
+    (include/msda_b200.h, Conventions).  Accepts the reference's materialised (N,T2,S,C) bool tensor
+    (models/model.py:156-157), a channel-expanded view (stride 0 in C) or a per-pixel (N,T2,S[,1]) mask."""
+    if mask is None:
+        return None, 0, 0
+    if mask.dtype != torch.bool:
+        raise RuntimeError("input_padding_mask must be a bool tensor")
+    if mask.dim() == 3:
+        mask = mask.unsqueeze(-1)
+    if mask.dim() != 4 or tuple(mask.shape[:3]) != (N, T2, S) or mask.shape[3] not in (1, C):
+        raise RuntimeError("input_padding_mask must be (N,T2,S,C), (N,T2,S,1) or (N,T2,S)")
+    if mask.shape[3] == 1:
+        mask = mask.expand(N, T2, S, C)
+    sn, st, ss, sc = mask.stride()
+    rows_ok = (S == 1 or ss > 0) and (T2 == 1 or st == S * ss) and (N == 1 or sn == T2 * S * ss)
+    if not (rows_ok and sc in (0, 1) and (sc == 0 or (ss % 4 == 0 and mask.data_ptr() % 4 == 0))):
+        mask = mask.contiguous()
+        ss, sc = C, 1
+    return mask, (ss if S > 1 else max(ss, 1)), sc
+
+
+def prefers_presum(T2: int, T1: int, n_frame: int, S: int, L: int, Lq: int, P: int) -> bool:
+    """True when summing the neighbour frames first (one streaming pass) beats gathering each of them."""
+    return bool(capi.lib().msda_snippet_prefers_presum(T2, T1, int(n_frame), S, L, Lq, P))
+
+
+def num_slots(T1: int, n_frame: int) -> int:
+    return (T1 if T1 < n_frame else n_frame) + (1 if T1 > n_frame else 0)
+
+
+def _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref, n_frame,
+                  presummed=False, T2=None):
     for t, name in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
                     (proj, "proj"), (ref, "reference_points")):
         _require_cuda(t, name)
     if value.dim() != 5 or proj.dim() != 4 or ref.dim() != 5:
         raise RuntimeError("expected value (N,T2,S,M,D), proj (N,T1,Lq,3*M*L*P), reference_points (N,T1,Lq,L,2)")
-    N, T2, S, M, D = value.shape
+    N, F, S, M, D = value.shape
     L = spatial_shapes.shape[0]
     Np, T1, Lq, W = proj.shape
     if Np != N or W % (3 * M * L) != 0:
         raise RuntimeError("proj must be (N,T1,Lq,3*M*L*P): [offsets (M,L,P,2) | logits (M,L,P)] per query")
     P = W // (3 * M * L)
-    if tuple(ref.shape) != (N, T1, Lq, L, 2) or tuple(spatial_shapes.shape) != (L, 2):
-        raise RuntimeError("reference_points must be (N,T1,Lq,L,2) and spatial_shapes (L,2)")
-    if not snippet_supported(M, D, L, P, value.dtype):
+    if tuple(ref.shape) != (N, T1, Lq, L, 2) or tuple(spatial_shapes.shape) != (L, 2) or level_start_index.numel() != L:
+        raise RuntimeError("reference_points must be (N,T1,Lq,L,2), spatial_shapes (L,2), level_start_index (L,)")
+    if not snippet_supported(M, D, L, P, value.dtype, S, N * T1):
         raise RuntimeError("fused snippet attention needs float32 / bfloat16 value, D % 16 == 0, D <= 128, L*P <= 32")
     if proj.dtype != torch.float32 or ref.dtype != torch.float32:
         raise RuntimeError("proj and reference_points must be float32")
     for b, n in ((offsets_bias, 2 * M * L * P), (logits_bias, M * L * P)):
         if b is not None and (not b.is_cuda or b.dtype != torch.float32 or b.numel() != n or not b.is_contiguous()):
             raise RuntimeError("biases must be contiguous float32 CUDA tensors of 2*M*L*P / M*L*P elements")
+    if presummed:
+        if F != num_slots(T1, n_frame) or not value.is_contiguous():
+            raise RuntimeError("presummed value must be a contiguous (N, slots, S, M, D) tensor")
+    else:
+        T2 = F
     if not (0 < n_frame <= T2):
         raise RuntimeError("n_frame must be in (0, T2]")
     _require_contiguous(proj, "proj")
@@ -450,99 +454,176 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-@torch.library.custom_op("snipper_b200::snippet_forward_packed", mutates_args=())
-def snippet_forward_packed(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, proj: Tensor,
-                           offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
-                           reference_points: Tensor, n_frame: int, value_mask: Optional[Tensor] = None) -> Tensor:
+def _frame_sum(value, mask, mrs, mcs, T1, n_frame):
+    """(N,T2,S,M,D) -> (N,slots,S,M,D): masked neighbour-frame sums, one slot per query frame."""
+    N, T2, S, M, D = value.shape
+    sn, st = _value_strides5(value)
+    vsum = torch.empty((N, num_slots(T1, n_frame), S, M, D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device), _Launch("frame_sum", (N, T2, T1, S, M * D), value.device):
+        status = capi.lib().msda_frame_sum(value.data_ptr(), _ptr(mask), vsum.data_ptr(), N, T2, T1, int(n_frame), S,
+                                           M * D, sn, st, mrs, mcs, _DTYPES[value.dtype], _stream(value.device))
+    capi.check(status, "msda_frame_sum")
+    return vsum
+
+
+@torch.library.custom_op("snipper_b200::snippet_attn", mutates_args=())
+def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor, level_start_index: Tensor,
+                 proj: Tensor, offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
+                 reference_points: Tensor, n_frame: int, presum: bool) -> Tuple[Tensor, Tensor]:
+    """The whole per-frame loop of the reference module (ms_deform_attn.py:116-117,126-225) for one layer.
+
+    value (N,T2,S,M,D) is the raw ``value_proj`` output; ``value_mask`` the padding mask over it (any layout
+    ``mask_layout`` accepts) or None; proj (N,T1,Lq,3*M*L*P) = [offsets | logits] without biases.
+    Returns (out (N,T1,Lq,M*D), carry): carry is the presummed value (N,slots,S,M,D) when ``presum`` -- the
+    only form of value the backward needs -- and an empty tensor otherwise."""
     N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
                                                  logits_bias, reference_points, n_frame)
-    sn, st = _value_strides5(value)
+    mask, mrs, mcs = mask_layout(value_mask, N, T2, S, M * D)
     ref, rsn, rst = _ref_strides(reference_points)
     mlp = M * L * P
     out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device), _Launch("snippet_forward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
+    dims = (N, T2, T1, S, M, D, L, Lq, P)
+    if presum:
+        carry = _frame_sum(value, mask, mrs, mcs, T1, n_frame)
+        src, sn, st, kmask, flags, tag = carry, 0, 0, None, capi.MSDA_FLAG_PRESUMMED, "snippet_forward_presummed"
+    else:
+        carry = value.new_empty((0,))
+        sn, st = _value_strides5(value)
+        src, kmask, flags, tag = value, mask, 0, "snippet_forward"
+    with torch.cuda.device(value.device), _Launch(tag, dims, value.device):
         status = capi.lib().msda_snippet_forward(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            src.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), out.data_ptr(),
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
-            _ptr(offsets_bias), _ptr(logits_bias), _DTYPES[value.dtype], _stream(value.device))
+            _ptr(offsets_bias), _ptr(logits_bias), _ptr(kmask), mrs, mcs,
+            _DTYPES[value.dtype], flags, _stream(value.device))
     capi.check(status, "msda_snippet_forward")
-    return out
+    return out, carry
 
 
-@snippet_forward_packed.register_fake
-def _(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points, n_frame,
-      value_mask=None):
+@snippet_attn.register_fake
+def _(value, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points,
+      n_frame, presum):
     N, T2, S, M, D = value.shape
-    return value.new_empty((N, proj.shape[1], proj.shape[2], M * D))
+    out = value.new_empty((N, proj.shape[1], proj.shape[2], M * D))
+    if presum:
+        return out, value.new_empty((N, num_slots(proj.shape[1], n_frame), S, M, D))
+    return out, value.new_empty((0,))
 
 
-@torch.library.custom_op("snipper_b200::snippet_backward_packed", mutates_args=())
-def snippet_backward_packed(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, proj: Tensor,
-                            offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
-                            reference_points: Tensor, grad_output: Tensor, n_frame: int,
-                            value_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-    """Returns (grad_value, grad_proj): grad_proj has proj's layout [grad_offsets | grad_logits]."""
-    N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
-                                                 logits_bias, reference_points, n_frame)
+@torch.library.custom_op("snipper_b200::snippet_attn_backward", mutates_args=())
+def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor,
+                          level_start_index: Tensor, proj: Tensor, offsets_bias: Optional[Tensor],
+                          logits_bias: Optional[Tensor], reference_points: Tensor, grad_output: Tensor,
+                          n_frame: int, presum: bool, n_src_frames: int, deterministic: bool) -> Tuple[Tensor, Tensor]:
+    """Returns (grad_value (N,T2,S,M,D) in value's dtype, grad_proj with proj's layout [grad_offsets | grad_logits]).
+    ``value_or_vsum`` is what the forward carried: the presummed value when ``presum``, else value itself."""
+    N, T2, T1, S, M, D, L, Lq, P = _check_packed(value_or_vsum, spatial_shapes, level_start_index, proj,
+                                                 offsets_bias, logits_bias, reference_points, n_frame,
+                                                 presummed=presum, T2=n_src_frames)
     _require_cuda(grad_output, "grad_output")
     _require_contiguous(grad_output, "grad_output")
-    sn, st = _value_strides5(value)
+    if grad_output.dtype != value_or_vsum.dtype or grad_output.numel() != N * T1 * Lq * M * D:
+        raise RuntimeError("grad_output must be (N,T1,Lq,M*D) in value's dtype")
+    dev, dt = value_or_vsum.device, value_or_vsum.dtype
+    mask, mrs, mcs = mask_layout(value_mask, N, T2, S, M * D)
     ref, rsn, rst = _ref_strides(reference_points)
     mlp = M * L * P
-    grad_value = torch.empty((N, T2, S, M, D), dtype=torch.float32, device=value.device)  # fp32 accumulation
     grad_proj = torch.empty_like(proj)
-    with torch.cuda.device(value.device), _Launch("snippet_backward", (N, T2, T1, S, M, D, L, Lq, P), value.device):
-        status = capi.lib().msda_snippet_backward(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+    dims = (N, T2, T1, S, M, D, L, Lq, P)
+    L_ = capi.lib()
+    if deterministic:
+        raise RuntimeError("deterministic fused backward: not built yet")
+    if presum:
+        slots = value_or_vsum.shape[1]
+        gsum = torch.empty((N, slots, S, M, D), dtype=torch.float32, device=dev)   # fp32 accumulation
+        with torch.cuda.device(dev), _Launch("snippet_backward_presummed", dims, dev, 2):
+            status = L_.msda_snippet_backward(
+                value_or_vsum.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
+                gsum.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
+                N, T2, T1, int(n_frame), S, M, D, L, Lq, P, 0, 0, rsn, rst, 3 * mlp, 3 * mlp,
+                _ptr(offsets_bias), _ptr(logits_bias), None, 0, 0, _DTYPES[dt], capi.MSDA_FLAG_PRESUMMED, _stream(dev))
+        capi.check(status, "msda_snippet_backward")
+        grad_value = torch.empty((N, T2, S, M, D), dtype=dt, device=dev)
+        with torch.cuda.device(dev), _Launch("frame_unsum", (N, T2, T1, S, M * D), dev):
+            status = L_.msda_frame_unsum(gsum.data_ptr(), _ptr(mask), grad_value.data_ptr(), N, T2, T1, int(n_frame), S,
+                                         M * D, mrs, mcs, _DTYPES[dt], _stream(dev))
+        capi.check(status, "msda_frame_unsum")
+        return grad_value, grad_proj
+    sn, st = _value_strides5(value_or_vsum)
+    grad_value = torch.empty((N, T2, S, M, D), dtype=torch.float32, device=dev)  # fp32 accumulation
+    with torch.cuda.device(dev), _Launch("snippet_backward", dims, dev, 2):
+        status = L_.msda_snippet_backward(
+            value_or_vsum.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
-            _ptr(offsets_bias), _ptr(logits_bias), _DTYPES[value.dtype], 0, _stream(value.device))
+            _ptr(offsets_bias), _ptr(logits_bias), _ptr(mask), mrs, mcs, _DTYPES[dt], 0, _stream(dev))
     capi.check(status, "msda_snippet_backward")
-    _mask_grad_value(grad_value, value_mask, value.device)
-    if value.dtype != torch.float32:
-        grad_value = grad_value.to(value.dtype)
+    if dt != torch.float32:
+        grad_value = grad_value.to(dt)
     return grad_value, grad_proj
 
 
-@snippet_backward_packed.register_fake
-def _(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points, grad_output,
-      n_frame, value_mask=None):
-    return value.new_empty(value.shape), torch.empty_like(proj)
+@snippet_attn_backward.register_fake
+def _(value_or_vsum, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias,
+      reference_points, grad_output, n_frame, presum, n_src_frames, deterministic):
+    N, _, S, M, D = value_or_vsum.shape
+    return value_or_vsum.new_empty((N, n_src_frames, S, M, D)), torch.empty_like(proj)
 
 
-def _packed_setup_context(ctx, inputs, output):
-    value, spatial_shapes, level_start_index, proj, ob, lb, reference_points, n_frame, value_mask = inputs
-    ctx.n_frame = n_frame
+def _attn_setup_context(ctx, inputs, output):
+    value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, reference_points, n_frame, presum = inputs
+    out, carry = output
+    ctx.n_frame, ctx.presum, ctx.T2 = n_frame, bool(presum), value.shape[1]
     ctx.flags = (ob is not None, lb is not None, value_mask is not None)
-    ctx.save_for_backward(*[t for t in (value, spatial_shapes, level_start_index, proj, reference_points, ob, lb,
-                                        value_mask) if t is not None])
+    # the presummed value replaces value itself: the backward reads nothing else of it
+    ctx.save_for_backward(*[t for t in (carry if presum else value, spatial_shapes, level_start_index, proj,
+                                        reference_points, ob, lb, value_mask) if t is not None])
+    ctx.set_materialize_grads(False)
 
 
-def _packed_backward_formula(ctx, grad_output):
+def _attn_backward_formula(ctx, grad_output, grad_carry):
     saved = list(ctx.saved_tensors)
     value, spatial_shapes, level_start_index, proj, ref = saved[:5]
     rest = saved[5:]
     ob = rest.pop(0) if ctx.flags[0] else None
     lb = rest.pop(0) if ctx.flags[1] else None
     value_mask = rest.pop(0) if ctx.flags[2] else None
-    gv, gproj = torch.ops.snipper_b200.snippet_backward_packed(
-        value, spatial_shapes, level_start_index, proj, ob, lb, ref, grad_output.contiguous(), ctx.n_frame, value_mask)
-    N, T2, S, M, D = value.shape
+    if grad_output is None:
+        return (None,) * 10
+    gv, gproj = torch.ops.snipper_b200.snippet_attn_backward(
+        value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, ref, grad_output.contiguous(),
+        ctx.n_frame, ctx.presum, ctx.T2, _deterministic)
+    N, _, S, M, D = value.shape
     L = spatial_shapes.shape[0]
     mlp = proj.shape[-1] // 3
     P = mlp // (M * L)
     gob = glb = gref = None
-    if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+    if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
         col = gproj.sum(dim=(0, 1, 2))                       # bias gradients = column sums of the projection gradient
-        gob = col[:2 * mlp] if ctx.needs_input_grad[4] else None
-        glb = col[2 * mlp:] if ctx.needs_input_grad[5] else None
-    if ctx.needs_input_grad[6]:
+        gob = col[:2 * mlp] if ctx.needs_input_grad[5] else None
+        glb = col[2 * mlp:] if ctx.needs_input_grad[6] else None
+    if ctx.needs_input_grad[7]:
         goff = gproj[..., :2 * mlp].view(proj.shape[0], proj.shape[1], proj.shape[2], M, L, P, 2)
         wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
         gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
-    return gv, None, None, gproj, gob, glb, gref, None, None
+    return gv, None, None, None, gproj, gob, glb, gref, None, None
 
 
-snippet_forward_packed.register_autograd(_packed_backward_formula, setup_context=_packed_setup_context)
+snippet_attn.register_autograd(_attn_backward_formula, setup_context=_attn_setup_context)
+
+
+def snippet_attention(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor, level_start_index: Tensor,
+                      proj: Tensor, offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
+                      reference_points: Tensor, n_frame: int, presum: Optional[bool] = None) -> Tensor:
+    """Fused layer attention; picks the neighbour-frame strategy (``presum=None``) from the shapes."""
+    N, T2, S, M, D = value.shape
+    _, T1, Lq, W = proj.shape
+    L = spatial_shapes.shape[0]
+    if presum is None:
+        presum = prefers_presum(T2, T1, n_frame, S, L, Lq, W // (3 * M * L)) or (_deterministic and torch.is_grad_enabled())
+    out, _ = torch.ops.snipper_b200.snippet_attn(value, value_mask, spatial_shapes, level_start_index, proj,
+                                                 offsets_bias, logits_bias, reference_points, n_frame, bool(presum))
+    return out

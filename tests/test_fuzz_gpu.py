@@ -148,3 +148,52 @@ def test_random_shapes_deterministic_backward(seed):
     args = (c["value"].double(), c["shapes"], c["lsi"], c["loc"].double(), c["attn"].double())
     for got, want in zip(a, c_oracle.backward(*args, c["grad_out"].double())):
         assert rel_err(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_random_shapes_packed_layer_strategies_and_masks_vs_oracle(seed, dtype):
+    """The packed per-layer op on random geometry -- pre-summed neighbour frames and direct gather, per-channel
+    and per-pixel padding masks, biases in-kernel -- against the C oracle composed per (t1,t2)."""
+    from snipper_b200 import ops
+    from snippet_oracle import snippet_attention_oracle
+    rng = random.Random(5000 + seed)
+    L = rng.choice([1, 2, 3])
+    shapes = torch.as_tensor([(rng.randint(2, 9), rng.randint(2, 9)) for _ in range(L)], dtype=torch.long)
+    lsi = level_start_index(shapes)
+    S = int(shapes.prod(1).sum())
+    M, D, P = rng.choice([(8, 48, 4), (4, 32, 2), (2, 64, 8), (8, 16, 4), (2, 128, 8)])
+    N, n_frame, fut = rng.choice([1, 2]), rng.choice([1, 2, 3, 4]), rng.choice([0, 0, 1, 2])
+    T2 = n_frame + rng.choice([0, 0, 1])                 # source frames beyond n_frame only feed future queries
+    T1, Lq = n_frame + fut, rng.choice([1, 9, 33, S])
+    mlp = M * L * P
+    g = torch.Generator().manual_seed(200 + seed)
+    value = torch.randn(N, T2, S, M, D, generator=g).to(dtype)
+    proj = torch.cat((torch.randn(N, T1, Lq, 2 * mlp, generator=g) * 2.0, torch.randn(N, T1, Lq, mlp, generator=g)), -1)
+    ob, lb = torch.randn(2 * mlp, generator=g), torch.randn(mlp, generator=g)
+    ref = torch.rand(N, T1, Lq, L, 2, generator=g) * 1.2 - 0.1
+    pix = torch.rand(N, T2, S, generator=g) < 0.2
+    go = torch.randn(N, T1, Lq, M * D, generator=g).to(dtype)
+
+    leaves = [t.clone().requires_grad_(True) for t in (value.float(), proj, ob, lb, ref)]
+    want_out = snippet_attention_oracle(leaves[0], pix, shapes, lsi, leaves[1], leaves[2], leaves[3], leaves[4], n_frame)
+    want_out.backward(go.float())
+    want = [want_out.detach()] + [t.grad for t in leaves]
+
+    ftol, vtol, stol = (1e-5, 1e-4, 1e-4) if dtype == torch.float32 else (1e-2, 1e-2, 1e-4)
+    for presum in (True, False):
+        for per_pixel in (True, False):
+            lv = [t.to(DEV).requires_grad_(True) for t in (value, proj, ob, lb, ref)]
+            mask = pix.to(DEV) if per_pixel else pix[..., None].expand(N, T2, S, M * D).contiguous().to(DEV)
+            out = ops.snippet_attention(lv[0], mask, shapes.to(DEV), lsi.to(DEV), lv[1], lv[2], lv[3], lv[4], n_frame,
+                                        presum=presum)
+            out.backward(go.to(DEV))
+            got = [out.detach()] + [t.grad for t in lv]
+            tag = (presum, per_pixel)
+            assert rel_err(got[0], want[0]) < ftol, tag
+            assert rel_err(got[1], want[1]) < vtol, tag
+            # bf16 + pre-summed: the slot sums are themselves stored in bf16, so the fp32 gradients carry bf16-level error
+            st = 1e-2 if (presum and dtype == torch.bfloat16) else stol
+            for i in (2, 3, 4, 5):
+                assert rel_err(got[i], want[i]) < st, (tag, i)
+            assert float(got[1].float().cpu()[pix].abs().max()) == 0.0

@@ -36,8 +36,7 @@ def test_argument_validation_needs_no_gpu():
     assert L.msda_forward(8, 8, 8, 8, 8, 8, 1, 4, 2, 16, 1, 3, 2, 0, 64, 7, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
     # empty problems are a no-op
     assert L.msda_forward(0, 0, 0, 0, 0, 0, 0, 4, 2, 16, 1, 3, 2, 0, 64, 0, 0) == capi.MSDA_OK
-    assert L.msda_set_tuning(b"pairs_d48", 7) == capi.MSDA_ERR_INVALID_ARGUMENT
-    assert L.msda_set_tuning(b"pairs_d48", 16) == capi.MSDA_OK
+    assert not hasattr(L, "msda_set_tuning")   # stateless ABI: no entry point writes process state
     assert L.msda_backward_workspace_bytes(1, 100, 8, 48, 3, 100, 4, 0, 0) == 0
     assert L.msda_backward_workspace_bytes(1, 100, 8, 48, 3, 100, 4, 0, capi.MSDA_FLAG_DETERMINISTIC) > 0
 
@@ -50,10 +49,12 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert L.msda_masked_zero(0, 0, 16, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert L.msda_masked_zero(256, 256, 16, F64, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
     assert L.msda_masked_zero(256, 257, 16, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
-    # msda_snippet_forward(value, shapes, lsi, offsets, logits, ref, out, N,T2,T1,n_frame,S,M,D,L,Lq,P, strides x6, biases x2, dtype, stream)
-    def fwd(N=1, T2=4, T1=4, n_frame=4, S=100, M=8, D=48, Lv=3, Lq=10, P=4, ors=0, lrs=0, dtype=F32, ptr=256):
+    # msda_snippet_forward(value, shapes, lsi, offsets, logits, ref, out, N,T2,T1,n_frame,S,M,D,L,Lq,P, strides x6,
+    #                      biases x2, mask, mask row / col stride, dtype, flags, stream)
+    def fwd(N=1, T2=4, T1=4, n_frame=4, S=100, M=8, D=48, Lv=3, Lq=10, P=4, ors=0, lrs=0, dtype=F32, ptr=256,
+            mask=None, mrs=0, mcs=0, flags=0):
         return L.msda_snippet_forward(ptr, ptr, ptr, ptr, ptr, ptr, ptr, N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                      0, 0, 0, 0, ors, lrs, None, None, dtype, 0)
+                                      0, 0, 0, 0, ors, lrs, None, None, mask, mrs, mcs, dtype, flags, 0)
     assert fwd(N=0) == capi.MSDA_OK and fwd(Lq=0) == capi.MSDA_OK          # empty problems: nothing is launched
     assert fwd(n_frame=5) == capi.MSDA_ERR_INVALID_ARGUMENT                 # n_frame > T2
     assert fwd(D=40) == capi.MSDA_ERR_INVALID_ARGUMENT                      # D % 16 != 0
@@ -62,10 +63,34 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert fwd(ors=8 * 3 * 4 * 2 - 2) == capi.MSDA_ERR_INVALID_ARGUMENT     # rows would overlap
     assert fwd(ors=8 * 3 * 4 * 3 + 1) == capi.MSDA_ERR_INVALID_ARGUMENT     # odd row stride breaks the float2 loads
     assert fwd(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT                     # null pointers with work to do
-    # deterministic mode is per-call only
+    # padding mask: per-channel masks are read as 32-bit words; no mask together with presummed value
+    assert fwd(N=0, mask=257, mrs=384, mcs=1) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fwd(N=0, mask=256, mrs=386, mcs=1) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fwd(N=0, mask=256, mrs=384, mcs=2) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fwd(N=0, mask=257, mrs=1, mcs=0) == capi.MSDA_OK
+    assert fwd(N=0, mask=256, mrs=384, mcs=1, flags=capi.MSDA_FLAG_PRESUMMED) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fwd(N=0, flags=capi.MSDA_FLAG_PRESUMMED) == capi.MSDA_OK
+    assert fwd(N=0, flags=64) == capi.MSDA_ERR_INVALID_ARGUMENT
+    # the fused layer's deterministic mode is composed by the host from msda_frame_sum + msda_backward(DETERMINISTIC):
+    # the fused entry point itself rejects the flag as an invalid argument (not as a dtype problem)
     assert L.msda_snippet_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 4, 4, 4, 100, 8, 48, 3, 10, 4,
-                                   0, 0, 0, 0, 0, 0, None, None, F32, capi.MSDA_FLAG_DETERMINISTIC, 0) \
-        == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+                                   0, 0, 0, 0, 0, 0, None, None, None, 0, 0, F32, capi.MSDA_FLAG_DETERMINISTIC, 0) \
+        == capi.MSDA_ERR_INVALID_ARGUMENT
+    # neighbour-frame pre-summation: slot structure, strategy choice, validation
+    assert L.msda_snippet_num_slots(4, 4) == 4 and L.msda_snippet_num_slots(6, 4) == 5 and L.msda_snippet_num_slots(2, 4) == 2
+    assert L.msda_snippet_prefers_presum(4, 4, 4, 9875, 3, 9875, 4) == 1     # encoder: 10 frame pairs -> 4 gathers
+    assert L.msda_snippet_prefers_presum(4, 6, 4, 9875, 3, 60, 4) == 0       # decoder: 60 queries
+    assert L.msda_snippet_prefers_presum(1, 1, 1, 9875, 3, 9875, 4) == 0     # T = 1: nothing to sum
+    def fsum(N=1, T2=4, T1=4, n_frame=4, S=100, C=384, dtype=F32, ptr=256, mask=None, mrs=0, mcs=0):
+        return L.msda_frame_sum(ptr, mask, ptr, N, T2, T1, n_frame, S, C, 0, 0, mrs, mcs, dtype, 0)
+    assert fsum(N=0) == capi.MSDA_OK
+    assert fsum(N=0, C=6) == capi.MSDA_ERR_INVALID_ARGUMENT                   # rows are walked in 16-byte chunks
+    assert fsum(N=0, C=12, dtype=BF16) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fsum(N=0, n_frame=5) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fsum(N=0, dtype=F64) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert fsum(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert L.msda_frame_unsum(0, None, 0, 0, 4, 4, 4, 100, 384, 0, 0, F32, 0) == capi.MSDA_OK
+    assert L.msda_frame_unsum(0, None, 0, 1, 4, 4, 4, 100, 384, 0, 0, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
     # deterministic mode: 32-bit corner ids -> a clear error instead of a wrong answer
     assert L.msda_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 64, 9875, 8, 48, 12, 9875 * 4, 8, 0, 64, F32,
                            capi.MSDA_FLAG_DETERMINISTIC, 256, 1 << 40, 0) == capi.MSDA_ERR_TOO_LARGE
@@ -102,6 +127,33 @@ def test_fake_kernels_give_shapes_without_a_device():
     lg = torch.empty(2, 6, 7, 8, 3, 4, device="meta")
     ref = torch.empty(2, 6, 7, 3, 2, device="meta")
     assert torch.ops.snipper_b200.snippet_forward(v5, sh, lsi, off, lg, ref, 4).shape == (2, 6, 7, 384)
+    proj = torch.empty(2, 6, 7, 3 * 8 * 3 * 4, device="meta")
+    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, 4, True)
+    assert out.shape == (2, 6, 7, 384) and carry.shape == (2, 5, 50, 8, 48)      # 4 frame slots + the all-frames slot
+    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, 4, False)
+    assert out.shape == (2, 6, 7, 384) and carry.numel() == 0
+    gv, gp = torch.ops.snipper_b200.snippet_attn_backward(v5, None, sh, lsi, proj, None, None, ref, out, 4, False, 4, False)
+    assert gv.shape == v5.shape and gp.shape == proj.shape
+
+
+def test_mask_layout_accepts_reference_and_per_pixel_masks():
+    from snipper_b200.ops import mask_layout
+    N, T2, S, C = 2, 3, 5, 8
+    full = torch.zeros(N, T2, S, C, dtype=torch.bool)
+    m, rs, cs = mask_layout(full, N, T2, S, C)
+    assert (rs, cs) == (C, 1) and m.data_ptr() == full.data_ptr()               # the reference's materialised mask
+    pix = torch.zeros(N, T2, S, 1, dtype=torch.bool)
+    m, rs, cs = mask_layout(pix.expand(N, T2, S, C), N, T2, S, C)
+    assert (rs, cs) == (1, 0)                                                   # one byte per pixel
+    assert mask_layout(pix, N, T2, S, C)[1:] == (1, 0) and mask_layout(pix[..., 0], N, T2, S, C)[1:] == (1, 0)
+    odd = torch.zeros(N, T2, S, C + 1, dtype=torch.bool)[..., :C]               # row stride 9: not word-aligned
+    m, rs, cs = mask_layout(odd, N, T2, S, C)
+    assert (rs, cs) == (C, 1) and m.is_contiguous()
+    assert mask_layout(None, N, T2, S, C) == (None, 0, 0)
+    with pytest.raises(RuntimeError):
+        mask_layout(torch.zeros(N, T2, S, C), N, T2, S, C)                      # not bool
+    with pytest.raises(RuntimeError):
+        mask_layout(torch.zeros(N, T2, S + 1, C, dtype=torch.bool), N, T2, S, C)
 
 
 def test_module_contract_matches_reference_checkpoint_layout():
