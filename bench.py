@@ -12,10 +12,14 @@ Workload (BASELINE.json configs[1], the config the metric is quoted on):
   are stock cuDNN/cuBLAS (out of scope per north_star) in torch's default fp32 settings.
 
 Output: ONE JSON line (rank 0).  `value` = snippets/s with inputs resident in HBM; `e2e` = same
-through the public call with pinned-host inputs (H2D + D2H inside the timed region);
-`roofline` = the dominant kernel (fused encoder-layer forward) timed with CUDA events on its
-stream; `cpu_baseline` = the reference's PyTorch/grid_sample formulation (oracle port) on the
-host cores for a bounded sample.  --impl reference prints the CPU arm as its own line.
+through the public call (snipper_b200.GraphRunner) with pinned-host inputs (H2D + D2H inside the timed
+region); `roofline` = the dominant kernel (fused encoder-layer forward gather) timed with CUDA events on
+its stream, `roofline.kernels` = every kernel of the hot path the same way; `gpu_baseline` = the
+UNMODIFIED reference network (baseline/_ref) running its own per-(t1,t2) loop and its own vendored CUDA op
+recompiled for sm_100a (oracle/_ref) on the same GPU; `train` = BASELINE config 4 (forward + backward + clip
++ AdamW, batch 2 per GPU, DDP gradient all-reduce over NCCL when launched on N > 1 ranks); `cpu_baseline` =
+the reference's PyTorch/grid_sample formulation (oracle port) on the host cores for a bounded sample.
+--impl reference prints the CPU arm as its own line.
 """
 import argparse
 import json
@@ -171,6 +175,206 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------
+def kernel_table(per_kernel, steps, bf16):
+    """tag -> launches / avg us / algorithmic bytes / GB/s for every kernel of the hot path."""
+    e = 2 if bf16 else 4
+    rows = []
+    for (tag, dims), ms in sorted(per_kernel.items(), key=lambda kv: -sum(kv[1])):
+        avg = sum(ms) / len(ms)
+        nbytes = None
+        if tag.startswith("snippet_forward"):
+            nbytes = fused_layer_bytes(dims, e)
+        elif tag.startswith("snippet_backward"):
+            N, T2, T1, S, M, D, L, Lq, P = dims
+            samples = N * T1 * Lq * M * L * P
+            v = min(N * T2 * S * M * D, 4 * samples * D * 3)
+            nbytes = e * (v + N * T1 * Lq * M * D) + 4 * (v + 6 * samples)
+        elif tag == "frame_sum":          # reads T2 frames, writes one slot per query frame
+            N, T2, T1, S, C = dims
+            nbytes = e * N * S * C * (T2 + min(T1, T2) + (1 if T1 > T2 else 0))
+        elif tag == "frame_unsum":
+            N, T2, T1, S, C = dims
+            nbytes = N * S * C * (4 * (min(T1, T2) + (1 if T1 > T2 else 0)) + e * T2)
+        rows.append({"kernel": tag, "dims": "x".join(map(str, dims)), "launches_per_step": len(ms) / steps,
+                     "avg_us": round(avg * 1e3, 2), "ms_per_step": round(sum(ms) / steps, 4),
+                     "algorithmic_MB": None if nbytes is None else round(nbytes / 1e6, 2),
+                     "GBps": None if nbytes is None else round(nbytes / (avg * 1e-3) / 1e9, 1)})
+    return rows
+
+
+def source_fingerprint():
+    """Hash of the kernel sources: profiles/roofline_traffic.json is only quoted while it matches."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("msda_snippet.cu", "msda_fast.cuh", "msda_common.cuh", "msda_frames.cu"):
+        with open(os.path.join(ROOT, "snipper_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def recorded_traffic(key):
+    """dram__bytes of one launch of the dominant kernel from the committed ncu capture -- null (with the reason)
+    when the kernel sources changed since the capture, instead of silently quoting a stale number."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            rec = json.load(f)
+    except Exception:
+        return None, "no profiles/roofline_traffic.json"
+    if rec.get("source_fingerprint") != source_fingerprint():
+        return None, "kernel sources changed since the ncu capture (%s)" % rec.get("captured_in", "?")
+    return rec.get(key), rec.get("captured_in")
+
+
+def gpu_baseline_run(dev, steps=5, warmup=2):
+    """The reference's own GPU path on this box: the UNMODIFIED reference network (baseline/_ref, staged by
+    baseline/stage_reference.py) with --use_pytorch_deform 0, i.e. its per-(t1,t2) Python loop
+    (models/ops/modules/ms_deform_attn.py:130-225) calling its own vendored CUDA op, compiled in place for
+    sm_100a (oracle/_ref).  Eager: the reference synchronises the stream in every attention call (:112), so it
+    cannot be graph-captured.  None of this package's kernels run here."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "models", "ops", "modules")):
+        return {"unavailable": "baseline/_ref not staged (run __graft_entry__.build() where /root/reference exists)"}
+    from oracle.build_ref import load_ref
+    vendored = load_ref()
+    if vendored is None:
+        return {"unavailable": "oracle/_ref/MultiScaleDeformableAttention.so not built"}
+    import torchvision
+    real_version = torchvision.__version__
+    torchvision.__version__ = "0.9.0"            # reference util/misc.py:20-22 mis-parses "0.26"
+    sys.path.insert(0, ref_dir)
+    try:
+        import models.backbone as bb
+        bb.is_main_process = lambda: False       # random init, no download (models/backbone.py:105-107)
+        import main as refmain
+        import models.ops.functions.ms_deform_attn_func as ref_func
+        ref_func.MSDA = vendored
+        args = refmain.get_args_parser().parse_args([])
+        args.device, args.hidden_dim, args.num_frames, args.num_future_frames = "cuda", 384, T, 0
+        args.enc_layers = args.dec_layers = 6
+        args.use_pytorch_deform = 0
+        from models.model import build_model
+        torch.manual_seed(42)
+        model = build_model(args)[0].to(dev).eval()
+        xs = [x.to(dev) for x in synthetic_snippets(2, seed=77)]
+        with torch.no_grad():
+            for i in range(warmup):
+                model(xs[i % 2])
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(steps):
+                out, _ = model(xs[i % 2])
+                pack_result(out)
+            e.record()
+            torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+        return {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "what": "unmodified reference network (baseline/_ref), use_pytorch_deform=0: its own per-(t1,t2) loop + its "
+                        "vendored CUDA op recompiled for sm_100a (oracle/_ref), eager, same GPU, same synthetic inputs shape"}
+    except Exception as ex:  # a baseline must never take the product's line down
+        return {"unavailable": "reference GPU path failed: %r" % (ex,)}
+    finally:
+        torchvision.__version__ = real_version
+        if ref_dir in sys.path:
+            sys.path.remove(ref_dir)
+        for name in [n for n in sys.modules if n == "main" or n.split(".")[0] in ("models", "util", "datasets", "engine",
+                                                                                 "eval_utils", "dataset_class")]:
+            mod = sys.modules.get(name)
+            if getattr(mod, "__file__", None) and ref_dir in str(mod.__file__):
+                del sys.modules[name]
+
+
+def synthetic_loss(out):
+    """Dense loss over every prediction head (the Hungarian criterion is CPU scipy code outside the hot path)."""
+    loss = out["pred_kpts2d"].square().mean() + out["pred_depth"].square().mean() + out["pred_logits"].square().mean()
+    for h in out["heatmaps"]:
+        loss = loss + h.square().mean()
+    for aux in out.get("aux_outputs", []):
+        loss = loss + aux["pred_kpts2d"].square().mean() + aux["pred_depth"].square().mean() + aux["pred_logits"].square().mean()
+    return loss
+
+
+def train_run(dev, rank, world, local_rank, steps=8, warmup=3, batch=2):
+    """BASELINE config 4: Snipper T=4 training step, batch 2 per GPU, as the reference's train_one_epoch
+    (engine.py:36-79: forward, loss, backward, clip_grad_norm_(0.1), AdamW.step); stock DDP when world > 1
+    (main.py:184).  Returns the per-rank dict (rank 0 prints it)."""
+    import torch.distributed as dist
+    import snipper_b200
+    from snipper_b200 import ops, sharding
+    from snipper_b200.harness.snipper_net import build_snipper
+    torch.manual_seed(42)
+    model = build_snipper(snipper_b200.MSDeformAttn).to(dev).train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)   # reference main.py:206-207
+    g = torch.Generator().manual_seed(2000 + rank)
+    xs = [torch.rand(batch, 3 * T, H, W, generator=g).to(dev) for _ in range(2)]
+
+    def step(i, sync=True):
+        import contextlib
+        ctx = net.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+        with ctx:
+            out, _ = net(xs[i % 2])
+            loss = synthetic_loss(out)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.1)                # reference engine.py:75
+        opt.step()
+        return loss
+
+    def timed(n, sync=True):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(n):
+            step(i, sync)
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return sharding.max_over_ranks(s.elapsed_time(e), dev) / n
+
+    for i in range(warmup):
+        step(i)
+    ms = timed(steps)
+    res = {"metric": "train_snippets_per_sec_T4_600x800", "value": world * batch / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms, "steps": steps, "batch_per_gpu": batch, "dtype": "f32",
+           "parallelism": ("DDP x%d, NCCL gradient all-reduce" % world) if world > 1 else "single GPU",
+           "loss": "synthetic dense loss over all heads; fwd + bwd + clip_grad_norm_(0.1) + AdamW"}
+    if world > 1:
+        # what the collective costs: the same step without gradient sync, and the all-reduce on its own
+        ms_nosync = timed(max(steps // 2, 2), sync=False)
+        n_grad = sum(p.numel() for p in params)
+        buf = torch.empty(n_grad, device=dev)
+        for _ in range(2):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            dist.all_reduce(buf)
+        e.record()
+        torch.cuda.synchronize()
+        ar_ms = sharding.max_over_ranks(s.elapsed_time(e), dev) / 5
+        res.update({"ms_per_step_without_gradient_sync": ms_nosync, "allreduce_exposed_ms": ms - ms_nosync,
+                    "allreduce_alone_ms": ar_ms, "allreduce_MB": n_grad * 4 / 1e6,
+                    "allreduce_busbw_GBps": 2 * (world - 1) / world * n_grad * 4 / (ar_ms * 1e-3) / 1e9})
+    ops.STATS.reset()
+    ops.STATS.timing = True
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    ops.STATS.timing = False
+    per = ops.STATS.kernel_ms()
+    msda_ms = sum(sum(v) for v in per.values()) / 2
+    res.update({"msda_ms_per_step": msda_ms, "msda_share": msda_ms / ms, "msda_kernels": kernel_table(per, 2, False)})
+    del net, model, opt
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,6 +383,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"],
                     help="NOT the headline: 'tf32' lets cuBLAS use TF32 tensor cores for the stock Linear layers, "
                          "'bf16' runs the network under torch.autocast(bfloat16) (bf16 GEMMs, bf16 MSDA gathers). "
@@ -202,17 +408,20 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import snipper_b200
-    from snipper_b200 import ops
+    from snipper_b200 import ops, sharding
     from snipper_b200.harness.snipper_net import build_snipper
 
     args.warmup = max(args.warmup, 3)
     if args.precision == "tf32":
         torch.backends.cuda.matmul.allow_tf32 = True
+    bf16 = args.precision == "bf16"
     import contextlib
-    autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if args.precision == "bf16" else contextlib.nullcontext
+    autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if bf16 else contextlib.nullcontext
     torch.manual_seed(42)  # reference main.py:48
     model = build_snipper(snipper_b200.MSDeformAttn).to(dev).eval()
-    host = [x.pin_memory() for x in synthetic_snippets(N_INPUTS, seed=1000 + rank)]  # every rank its own shard
+    # snippet sharding: every rank takes its own contiguous slice of the job's snippets (no data-path collective)
+    lo, hi = sharding.shard_range(N_INPUTS * world, rank, world)
+    host = [x.pin_memory() for x in synthetic_snippets(hi - lo, seed=1000 + rank)]
     resident = [x.to(dev) for x in host]
     h2d_bytes = host[0].numel() * host[0].element_size()
 
@@ -221,56 +430,36 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # ---- the public call: a graphed runner over "snippet in -> packed predictions out" ----
+    def forward_packed(x):
+        out, _ = model(x)
+        return pack_result(out).float()
 
-    # ---- build the step functions -------------------------------------------------------
-    use_graph = not args.no_graph
-    static_in = torch.empty_like(resident[0])
     with torch.no_grad(), autocast():
-        for i in range(2):  # lazy init (cuDNN autotune, cuBLAS handles) before capture
-            out, _ = model(resident[i])
-            result = pack_result(out).float()
+        result = forward_packed(resident[0])
     d2h_bytes = result.numel() * result.element_size()
     host_out = torch.empty(result.shape, dtype=result.dtype).pin_memory()
-    graph, launches_per_step = None, None
-    ops.STATS.reset()
-    if use_graph:
+    runner, launches_per_step = None, None
+    if not args.no_graph:
         try:
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.no_grad(), autocast(), torch.cuda.graph(graph):
-                out, _ = model(static_in)
-                static_result = pack_result(out).float()
-            launches_per_step = ops.STATS.launches
+            runner = snipper_b200.GraphRunner(forward_packed, warmup=2, autocast_dtype=torch.bfloat16 if bf16 else None)
+            launches_per_step = runner.launches_per_replay(resident[0])
         except Exception as e:  # fall back to eager timing, say so in config
             print("[bench] CUDA graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
-            graph, use_graph = None, False
+            runner = None
             torch.cuda.synchronize()
 
-    def step_resident(i):
+    def call(x):
+        if runner is not None:
+            return runner(x)
         with torch.no_grad(), autocast():
-            if graph is not None:
-                static_in.copy_(resident[i % N_INPUTS])  # device->device, keeps inputs rotating
-                graph.replay()
-                return static_result
-            out, _ = model(resident[i % N_INPUTS])
-            return pack_result(out).float()
+            return forward_packed(x.to(dev, non_blocking=True))
+
+    def step_resident(i):
+        return call(resident[i % len(resident)])
 
     def step_e2e(i):
-        with torch.no_grad(), autocast():
-            if graph is not None:
-                static_in.copy_(host[i % N_INPUTS], non_blocking=True)
-                graph.replay()
-                host_out.copy_(static_result, non_blocking=True)
-            else:
-                x = host[i % N_INPUTS].to(dev, non_blocking=True)
-                out, _ = model(x)
-                host_out.copy_(pack_result(out).float(), non_blocking=True)
+        host_out.copy_(call(host[i % len(host)]), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
         return host_out
 
@@ -284,7 +473,7 @@ def main():
             step_fn(warmup + i)
         e.record()
         barrier()
-        return max_over_ranks(s.elapsed_time(e))
+        return sharding.max_over_ranks(s.elapsed_time(e), dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -298,12 +487,12 @@ def main():
     if launches_per_step is None:
         launches_per_step = eager_launches // (args.steps + args.warmup)
 
-    # ---- roofline of the dominant kernel: events around every fused-layer launch, eager steps ----
+    # ---- roofline: events around every launch of the hot path, eager steps after the timed region ----
     ops.STATS.reset()
     ops.STATS.timing = True
     with torch.no_grad(), autocast():
         for i in range(args.steps):
-            model(resident[i % N_INPUTS])
+            model(resident[i % len(resident)])
     torch.cuda.synchronize()
     ops.STATS.timing = False
     per_kernel = ops.STATS.kernel_ms()
@@ -312,23 +501,30 @@ def main():
     dom_avg_ms = sum(dom_ms) / len(dom_ms)
     msda_ms_per_step = sum(sum(v) for v in per_kernel.values()) / args.steps
     peak, peak_src = measured_peak()
-    alg_bytes = fused_layer_bytes(dom_dims, e=2 if args.precision == "bf16" else 4)
+    e_bytes = 2 if bf16 else 4
+    alg_bytes = fused_layer_bytes(dom_dims, e=e_bytes)
     achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
-    e_bytes = 2 if args.precision == "bf16" else 4
-    gathered = fused_layer_gathered_bytes(dom_dims, model.num_frames, e_bytes)
+    presummed = dom_tag.endswith("presummed")
+    # bytes that cross the L1 data pipe: 4 corners x D channels per sample and GATHERED frame (one per query frame
+    # when the neighbour frames are pre-summed, |nb(t1)| otherwise)
+    N_, T2_, T1_, S_, M_, D_, L_, Lq_, P_ = dom_dims
+    gathered = (N_ * T1_ * Lq_ * M_ * L_ * P_ * 4 * D_ * e_bytes) if presummed else \
+        fused_layer_gathered_bytes(dom_dims, model.num_frames, e_bytes)
     ceiling = measured_l1_gather_ceiling()
-    on_chip = {"what": "bytes gathered through L1 per launch (4 corners x D channels per sample and neighbour frame) / launch time, "
-                       "against the measured L1 gather ceiling for 192-byte slices (tools/micro/l1_tex_vs_ldg.cu): the resource "
-                       "that actually bounds this kernel (ncu: l1tex data-pipe wavefronts 85-88 % of peak, DRAM 7 %)",
+    on_chip = {"what": "bytes gathered through L1 per launch / launch time, against the measured L1 gather ceiling for 192-byte "
+                       "slices (tools/micro/l1_tex_vs_ldg.cu): the on-chip resource this gather runs against",
                "gathered_bytes_per_launch": gathered, "achieved_TBps": gathered / (dom_avg_ms * 1e-3) / 1e12,
                "measured_ceiling_TBps": ceiling,
                "frac": (gathered / (dom_avg_ms * 1e-3) / 1e12 / ceiling) if ceiling else None}
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get("snippet_forward_encoder_dram_bytes_per_launch")
-    except Exception:
-        pass
+    traffic, traffic_src = recorded_traffic("snippet_forward_presummed_encoder_dram_bytes_per_launch" if presummed
+                                            else "snippet_forward_encoder_dram_bytes_per_launch")
+
+    graphed = runner is not None
+    train = None
+    if not args.no_train and args.precision == "fp32":
+        runner = None
+        torch.cuda.empty_cache()
+        train = train_run(dev, rank, world, local_rank)
 
     if rank != 0:
         if world > 1:
@@ -344,21 +540,29 @@ def main():
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32-matmul (informational)", "bf16": "bf16-autocast (informational)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "snippets_per_gpu_per_step": 1, "parallelism": "snippet-sharded x%d, no collective" % world,
-                   "launch": "cuda_graph_replay" if graph is not None else "eager",
-                   "l2": "working set per step (171 MB weights + >1 GB activations) exceeds the 126 MB L2; %d distinct inputs rotated" % N_INPUTS,
+                   "launch": "cuda_graph_replay (snipper_b200.GraphRunner)" if graphed else "eager",
+                   "l2": "working set per step (171 MB weights + >1 GB activations) exceeds the 126 MB L2; %d distinct inputs rotated" % len(resident),
                    "weights": "random init (seed 42): sampling offsets are the fixed per-head grid, best-case gather locality",
+                   "precision_note": "fp32 = torch defaults: fp32 SIMT GEMMs for the Linear layers, cuDNN convolutions may use TF32 "
+                                     "(torch.backends.cudnn.allow_tf32 default); the CPU arm is strict fp32",
                    "msda_ms_per_step_eager_events": msda_ms_per_step},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "msda_snippet_fwd_kernel<12,16> (%s %s)" % (dom_tag, "x".join(map(str, dom_dims))),
+        "roofline": {"bound": "hbm", "kernel": "msda_snippet_fwd_kernel<float,12,16,1536,%s> (%s %s)" % (
+                         "presummed" if presummed else "direct", dom_tag, "x".join(map(str, dom_dims))),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": dom_avg_ms, "launches_timed": len(dom_ms),
                      "how": "CUDA events on the launching stream around each launch, eager steps after the timed region",
-                     "on_chip": on_chip},
+                     "on_chip": on_chip, "kernels": kernel_table(per_kernel, args.steps, bf16)},
     }
+    if train is not None:
+        line["train"] = train
+    if world == 1 and not args.no_gpu_baseline:
+        line["gpu_baseline"] = gpu_baseline_run(dev)
     if world == 1 and not args.no_cpu_baseline:
         times, cores = cpu_reference_run(1, 0)
         v = len(times) / sum(times)

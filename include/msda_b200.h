@@ -17,6 +17,8 @@
  *   msda_snippet_backward      models/ops/modules/ms_deform_attn.py:126-225 (offset normalisation,
  *                              softmax over levels x points x neighbour frames, one op call per
  *                              (t1,t2) pair, sum over t2) fused into one launch per layer
+ *   msda_layer_tail         <- `x = x + dropout(Linear(..)); x = norm(x)` + `with_pos_embed` of the calling layers
+ *                              models/deformable_transformer.py:188-205,270-295 (opt-in)
  *   msda_frame_sum /        <- value.masked_fill(input_padding_mask, 0) (ms_deform_attn.py:116-117) and
  *   msda_frame_unsum           the stack(-1).sum(-1) over neighbour frames (:225), moved IN FRONT of the
  *                              gather by linearity of the op in `value` (one gather per query frame)
@@ -172,6 +174,11 @@ MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shap
  * MSDA_FLAG_ACCUMULATE_VALUE), grad_offsets like offsets, grad_logits like logits (same row strides).
  * The gradient w.r.t. reference_points is sum_{m,p} grad_offsets * (W_l,H_l), the gradients of the biases
  * are the sums of grad_offsets / grad_logits over rows; both are left to the caller.
+ * MSDA_FLAG_DETERMINISTIC (with MSDA_FLAG_PRESUMMED, MSDA_DTYPE_F32): bit-reproducible run to run -- grad_offsets /
+ * grad_logits come from the same kernel with its scatter compiled out (no atomics), grad_value from the two-pass
+ * count / fill / ordered-reduce of msda_backward's deterministic mode run over the slots; needs a workspace of
+ * msda_snippet_backward_workspace_bytes(...) bytes.  msda_frame_sum / msda_frame_unsum are deterministic by
+ * construction, so the whole fused layer is.
  */
 MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           const int64_t *level_start_index, const void *offsets, const void *logits,
@@ -185,7 +192,12 @@ MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_sha
                           int64_t offsets_row_stride, int64_t logits_row_stride,
                           const void *offsets_bias, const void *logits_bias,
                           const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
-                          int dtype, unsigned flags, void *stream);
+                          int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Bytes of (256-byte aligned) workspace msda_snippet_backward needs: 0 unless MSDA_FLAG_DETERMINISTIC. */
+MSDA_API size_t msda_snippet_backward_workspace_bytes(int batch, int n_query_frames, int n_frame, int spatial_size,
+                                                      int num_heads, int channels, int num_levels, int num_query,
+                                                      int num_point, int dtype, unsigned flags);
 
 /*
  * Neighbour-frame pre-summation.  The op is linear in `value` and the reference uses the same sampling
@@ -211,6 +223,19 @@ MSDA_API int msda_frame_unsum(const void *grad_vsum, const unsigned char *value_
                               int batch, int n_src_frames, int n_query_frames, int n_frame,
                               int spatial_size, int row_elems,
                               int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream);
+
+/*
+ * Layer tail: what follows every attention / FFN block of the reference's encoder and
+ * decoder layers (models/deformable_transformer.py:204-205,194-198,294-295,270-274) and precedes the next attention
+ * block (with_pos_embed, :188-190,:202,:292), in ONE pass over the activations instead of five:
+ *     out          = LayerNorm(residual + (y + bias)) * gamma + beta        (rows, cols)
+ *     out_plus_pos = out + pos                                              (optional, both or neither)
+ * y = raw GEMM output of the block's last Linear (bias not added yet; bias may be NULL), every row dense.
+ * MSDA_DTYPE_F32; cols % 128 == 0, cols <= 1024; inference only (no gradient formula is provided).
+ */
+MSDA_API int msda_layer_tail(const void *y, const void *bias, const void *residual, const void *gamma, const void *beta,
+                             const void *pos, void *out, void *out_plus_pos, int64_t rows, int cols, float eps,
+                             int dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -17,9 +17,12 @@ from . import capi, ops  # noqa: F401
 from .functions import MSDeformAttnFunction, ms_deform_attn
 from .modules import MSDeformAttn
 from .ops import is_deterministic, set_deterministic
+from .runtime import GraphRunner
+from .layers import disable_fused_layer_tails, enable_fused_layer_tails
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "ms_deform_attn", "set_deterministic",
-           "is_deterministic", "install_extension_shim", "install_module"]
+           "is_deterministic", "install_extension_shim", "install_module", "GraphRunner",
+           "enable_fused_layer_tails", "disable_fused_layer_tails"]
 
 _SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 

@@ -30,8 +30,8 @@ MSDA_FLAG_PRESUMMED = 4
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_forward",
     "msda_backward", "msda_backward_workspace_bytes", "msda_masked_zero", "msda_snippet_forward",
-    "msda_snippet_backward", "msda_snippet_num_slots", "msda_snippet_prefers_presum", "msda_frame_sum",
-    "msda_frame_unsum",
+    "msda_snippet_backward", "msda_snippet_backward_workspace_bytes", "msda_snippet_num_slots", "msda_snippet_prefers_presum", "msda_frame_sum",
+    "msda_frame_unsum", "msda_layer_tail",
 )
 
 _lib = None
@@ -72,7 +72,9 @@ def lib():
     L.msda_snippet_forward.restype = i32
     L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp]
     L.msda_snippet_backward.restype = i32
-    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp]
+    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp, sz, vp]
+    L.msda_snippet_backward_workspace_bytes.restype = sz
+    L.msda_snippet_backward_workspace_bytes.argtypes = [i32] * 10 + [u32]
     L.msda_snippet_num_slots.restype = i32
     L.msda_snippet_num_slots.argtypes = [i32, i32]
     L.msda_snippet_prefers_presum.restype = i32
@@ -81,6 +83,8 @@ def lib():
     L.msda_frame_sum.argtypes = [vp, vp, vp] + [i32] * 6 + [i64, i64, i64, i32, i32, vp]
     L.msda_frame_unsum.restype = i32
     L.msda_frame_unsum.argtypes = [vp, vp, vp] + [i32] * 6 + [i64, i32, i32, vp]
+    L.msda_layer_tail.restype = i32
+    L.msda_layer_tail.argtypes = [vp] * 8 + [i64, i32, ctypes.c_float, i32, vp]
     if L.msda_abi_version() != MSDA_ABI_VERSION:
         raise RuntimeError("libmsda_b200.so ABI %d != binding ABI %d; rebuild" %
                            (L.msda_abi_version(), MSDA_ABI_VERSION))

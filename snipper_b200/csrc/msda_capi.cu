@@ -191,6 +191,19 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
         (float *)grad_sampling_loc, (float *)grad_attn_weight, d, s));
 }
 
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// the fused layer's backward as a per-call problem over N*T1 batch items whose grad_value frames are the slots
+static msda::OpDims snippet_det_dims(int batch, int n_query_frames, int n_frame, int spatial_size, int num_heads,
+                                     int channels, int num_levels, int num_query, int num_point)
+{
+    msda::OpDims od{batch * n_query_frames, spatial_size, num_heads, channels, num_levels, num_query, num_point, 0};
+    od.frame_q = n_query_frames;
+    od.frame_local = n_query_frames < n_frame ? n_query_frames : n_frame;
+    od.frame_slots = msda::snippet_num_slots(n_query_frames, n_frame);
+    return od;
+}
+
 static int check_mask(const unsigned char *mask, int64_t row_stride, int col_stride)
 {
     if (mask == nullptr) return MSDA_OK;
@@ -295,12 +308,13 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           int64_t offsets_row_stride, int64_t logits_row_stride,
                           const void *offsets_bias, const void *logits_bias,
                           const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
-                          int dtype, unsigned flags, void *stream)
+                          int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (flags & ~(MSDA_FLAG_PRESUMMED | MSDA_FLAG_ACCUMULATE_VALUE | MSDA_FLAG_DETERMINISTIC)) return MSDA_ERR_INVALID_ARGUMENT;
-    // the deterministic mode of the fused layer is composed from msda_frame_sum + msda_backward(DETERMINISTIC)
-    // by the host side (snipper_b200/ops.py); this entry point itself always scatters with vector reductions
-    if (flags & MSDA_FLAG_DETERMINISTIC) return MSDA_ERR_INVALID_ARGUMENT;
+    const bool deterministic = (flags & MSDA_FLAG_DETERMINISTIC) != 0;
+    // deterministic mode: two-pass grad_value over the pre-summed slots, float32
+    if (deterministic && !(flags & MSDA_FLAG_PRESUMMED)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (deterministic && dtype != MSDA_DTYPE_F32) return MSDA_ERR_UNSUPPORTED_DTYPE;
     msda::SnippetDims d;
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
@@ -310,6 +324,45 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int gframes = (flags & MSDA_FLAG_PRESUMMED) ? msda::snippet_num_slots(n_query_frames, n_frame) : n_src_frames;
     const size_t value_elems = (size_t)batch * gframes * spatial_size * num_heads * channels;
+    if (deterministic) {
+        // 32-bit corner / cell ids (checked before anything is enqueued)
+        const int64_t samples = (int64_t)batch * n_query_frames * num_query * num_heads * num_levels * num_point;
+        if (samples * 4 >= (int64_t)INT32_MAX || (int64_t)batch * gframes * spatial_size * num_heads >= (int64_t)INT32_MAX)
+            return MSDA_ERR_TOO_LARGE;
+        const msda::OpDims od = snippet_det_dims(batch, n_query_frames, n_frame, spatial_size, num_heads, channels,
+                                                 num_levels, num_query, num_point);
+        const size_t loc_bytes = align256(sizeof(float) * 2 * (size_t)samples), attn_bytes = align256(sizeof(float) * (size_t)samples);
+        const size_t need = loc_bytes + attn_bytes + msda::deterministic_workspace_bytes(od);
+        if (batch > 0 && num_query > 0 &&
+            (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u)))
+            return MSDA_ERR_WORKSPACE;
+        if (batch == 0) return MSDA_OK;
+        if (!grad_value || !aligned16(grad_value)) return MSDA_ERR_INVALID_ARGUMENT;
+        if (num_query == 0) {
+            if (flags & MSDA_FLAG_ACCUMULATE_VALUE) return MSDA_OK;
+            return cuda_status(cudaMemsetAsync(grad_value, 0, sizeof(float) * value_elems, s));
+        }
+        if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points ||
+            !grad_output || !grad_offsets || !grad_logits)
+            return MSDA_ERR_INVALID_ARGUMENT;
+        if (!aligned16(value) || !aligned16(grad_output) || (reinterpret_cast<uintptr_t>(offsets) & 7u) ||
+            (reinterpret_cast<uintptr_t>(grad_offsets) & 7u) || (reinterpret_cast<uintptr_t>(offsets_bias) & 7u))
+            return MSDA_ERR_INVALID_ARGUMENT;
+        unsigned char *ws = static_cast<unsigned char *>(workspace);
+        float *loc = reinterpret_cast<float *>(ws), *attn = reinterpret_cast<float *>(ws + loc_bytes);
+        // everything but grad_value: the fused backward kernel with its scatter compiled out
+        st = cuda_status(msda::launch_snippet_backward_noscatter_f32(
+            (const float *)value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
+            (const float *)reference_points, (const float *)grad_output, (float *)grad_offsets, (float *)grad_logits, d, s));
+        if (st != MSDA_OK) return st;
+        st = cuda_status(msda::launch_snippet_loc_attn(spatial_shapes, level_start_index, (const float *)offsets,
+                                                       (const float *)logits, (const float *)reference_points, loc, attn, d, s));
+        if (st != MSDA_OK) return st;
+        // grad_value: count / scan / fill / ordered reduce; every slot cell is written exactly once
+        return cuda_status(msda::launch_deterministic_grad_value_f32(
+            spatial_shapes, level_start_index, loc, attn, (const float *)grad_output, (float *)grad_value, od,
+            ws + loc_bytes + attn_bytes, s, (flags & MSDA_FLAG_ACCUMULATE_VALUE) != 0));
+    }
     if (!(flags & MSDA_FLAG_ACCUMULATE_VALUE) && value_elems > 0) {
         if (!grad_value) return MSDA_ERR_INVALID_ARGUMENT;
         st = cuda_status(cudaMemsetAsync(grad_value, 0, sizeof(float) * value_elems, s));
@@ -332,6 +385,18 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
         (const float *)value, spatial_shapes, level_start_index, (const float *)offsets,
         (const float *)logits, (const float *)reference_points, (const float *)grad_output,
         (float *)grad_value, (float *)grad_offsets, (float *)grad_logits, d, s));
+}
+
+size_t msda_snippet_backward_workspace_bytes(int batch, int n_query_frames, int n_frame, int spatial_size,
+                                             int num_heads, int channels, int num_levels, int num_query,
+                                             int num_point, int dtype, unsigned flags)
+{
+    if (!(flags & MSDA_FLAG_DETERMINISTIC) || dtype != MSDA_DTYPE_F32) return 0;
+    if (batch <= 0 || n_query_frames <= 0 || n_frame <= 0 || num_query <= 0) return 0;
+    const size_t samples = (size_t)batch * n_query_frames * num_query * num_heads * num_levels * num_point;
+    const msda::OpDims od = snippet_det_dims(batch, n_query_frames, n_frame, spatial_size, num_heads, channels,
+                                             num_levels, num_query, num_point);
+    return align256(sizeof(float) * 2 * samples) + align256(sizeof(float) * samples) + msda::deterministic_workspace_bytes(od);
 }
 
 int msda_snippet_num_slots(int n_query_frames, int n_frame)
@@ -412,6 +477,24 @@ int msda_frame_unsum(const void *grad_vsum, const unsigned char *value_mask, voi
     if (dtype == MSDA_DTYPE_F32 && !aligned16(grad_value)) return MSDA_ERR_INVALID_ARGUMENT;
     return cuda_status(msda::launch_frame_unsum(static_cast<const float *>(grad_vsum), value_mask, grad_value, d,
                                                 dtype == MSDA_DTYPE_BF16 ? 2 : 4, static_cast<cudaStream_t>(stream)));
+}
+
+int msda_layer_tail(const void *y, const void *bias, const void *residual, const void *gamma, const void *beta,
+                    const void *pos, void *out, void *out_plus_pos, int64_t rows, int cols, float eps, int dtype,
+                    void *stream)
+{
+    if (dtype != MSDA_DTYPE_F32) return MSDA_ERR_UNSUPPORTED_DTYPE;
+    if (rows < 0 || !msda::layer_tail_ok(cols) || !(eps >= 0.f)) return MSDA_ERR_INVALID_ARGUMENT;
+    if ((pos == nullptr) != (out_plus_pos == nullptr)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (rows == 0) return MSDA_OK;
+    const void *ptrs[] = {y, residual, gamma, beta, out};
+    for (const void *p : ptrs)
+        if (p == nullptr || !aligned16(p)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (!aligned16(bias) || !aligned16(pos) || !aligned16(out_plus_pos)) return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_layer_tail((const float *)y, (const float *)bias, (const float *)residual,
+                                               (const float *)gamma, (const float *)beta, (const float *)pos,
+                                               (float *)out, (float *)out_plus_pos, rows, cols, eps,
+                                               static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

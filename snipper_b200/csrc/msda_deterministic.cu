@@ -37,9 +37,12 @@ struct DetLayout {
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// frames of grad_value: one per batch item, or the fused layer's slots (see OpDims)
+inline int64_t dest_frames(const OpDims &d) { return d.frame_q > 0 ? (int64_t)(d.N / d.frame_q) * d.frame_slots : d.N; }
+
 DetLayout det_layout(const OpDims &d)
 {
-    const size_t cells = (size_t)d.N * d.S * d.M;
+    const size_t cells = (size_t)dest_frames(d) * d.S * d.M;
     const size_t corners = (size_t)d.N * d.Lq * d.M * d.L * d.P * 4;
     const size_t nblocks = (cells + kScanTile - 1) / kScanTile;
     DetLayout l;
@@ -60,7 +63,8 @@ __global__ void __launch_bounds__(256)
 det_count_fill_kernel(const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                       const float *__restrict__ loc, const float *__restrict__ attn,
                       int *__restrict__ count, int *__restrict__ cursor, const int *__restrict__ start,
-                      CornerRec *__restrict__ records, int S, int M, int L, int P, int Lq, int64_t total_samples)
+                      CornerRec *__restrict__ records, int S, int M, int L, int P, int Lq, int64_t total_samples,
+                      int frame_q, int frame_local, int frame_slots)
 {
     __shared__ LevelTable lv;
     load_level_table(lv, shapes, lsi, L, S);
@@ -73,6 +77,7 @@ det_count_fill_kernel(const int64_t *__restrict__ shapes, const int64_t *__restr
         const int m = (int)(pair % M);
         const int64_t n = pair / ((int64_t)Lq * M);
         const int l = lp / P;
+        const int64_t frame = frame_q > 0 ? (n / frame_q) * frame_slots + min((int)(n % frame_q), frame_local) : n;
         const Sample<float> s = make_sample<float>(loc[2 * si], loc[2 * si + 1], lv.H[l], lv.W[l], lv.start[l]);
         float w[4];
         if (FILL) {
@@ -82,7 +87,7 @@ det_count_fill_kernel(const int64_t *__restrict__ shapes, const int64_t *__restr
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (s.cell[k] < 0) continue;
-            const int64_t dest = (n * S + s.cell[k]) * M + m;
+            const int64_t dest = (frame * S + s.cell[k]) * M + m;
             if (!FILL) {
                 atomicAdd(count + dest, 1);
             } else {
@@ -339,9 +344,19 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
                                               const OpDims &d, void *workspace, cudaStream_t stream,
                                               bool accumulate)
 {
-    const int64_t cells = (int64_t)d.N * d.S * d.M;
+    cudaError_t e = launch_backward_no_scatter_f32(value, shapes, lsi, loc, attn, grad_out, grad_loc, grad_attn, d, stream);
+    if (e != cudaSuccess) return e;
+    return launch_deterministic_grad_value_f32(shapes, lsi, loc, attn, grad_out, grad_value, d, workspace, stream, accumulate);
+}
+
+cudaError_t launch_deterministic_grad_value_f32(const int64_t *shapes, const int64_t *lsi, const float *loc,
+                                                const float *attn, const float *grad_out, float *grad_value,
+                                                const OpDims &d, void *workspace, cudaStream_t stream,
+                                                bool accumulate)
+{
+    const int64_t cells = dest_frames(d) * d.S * d.M;
     const int64_t samples = (int64_t)d.N * d.Lq * d.M * d.L * d.P;
-    if (samples * 4 >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;  // corner ids are 32-bit
+    if (samples * 4 >= (int64_t)INT32_MAX || cells >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;  // 32-bit corner / cell ids
     const DetLayout lay = det_layout(d);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     int *count = reinterpret_cast<int *>(ws + lay.count);
@@ -349,9 +364,7 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
     int *start = reinterpret_cast<int *>(ws + lay.start);
     int *blocksums = reinterpret_cast<int *>(ws + lay.blocksums);
     CornerRec *records = reinterpret_cast<CornerRec *>(ws + lay.records);
-
-    cudaError_t e = launch_backward_no_scatter_f32(value, shapes, lsi, loc, attn, grad_out, grad_loc, grad_attn, d, stream);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
     if (cells == 0) return cudaSuccess;
     int *long_cells = reinterpret_cast<int *>(ws + lay.long_cells);
     // count, cursor and the long-list queue are adjacent regions: one memset clears all three
@@ -360,14 +373,16 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
     const int sample_blocks = (int)((samples + 255) / 256 < 148 * 32 ? (samples + 255) / 256 : 148 * 32);
     if (samples > 0)
         det_count_fill_kernel<false><<<sample_blocks, 256, 0, stream>>>(shapes, lsi, loc, attn, count, cursor, start,
-                                                                      records, d.S, d.M, d.L, d.P, d.Lq, samples);
+                                                                      records, d.S, d.M, d.L, d.P, d.Lq, samples,
+                                                                      d.frame_q, d.frame_local, d.frame_slots);
     const int nblocks = (int)((cells + kScanTile - 1) / kScanTile);
     scan_tiles_kernel<<<nblocks, kScanBlock, 0, stream>>>(count, start, blocksums, cells);
     scan_blocksums_kernel<<<1, 32, 0, stream>>>(blocksums, nblocks);
     scan_add_kernel<<<nblocks, kScanBlock, 0, stream>>>(start, blocksums, cells, nblocks);
     if (samples > 0)
         det_count_fill_kernel<true><<<sample_blocks, 256, 0, stream>>>(shapes, lsi, loc, attn, count, cursor, start,
-                                                                     records, d.S, d.M, d.L, d.P, d.Lq, samples);
+                                                                     records, d.S, d.M, d.L, d.P, d.Lq, samples,
+                                                                      d.frame_q, d.frame_local, d.frame_slots);
     const int64_t rblocks = (cells + kReduceWarps - 1) / kReduceWarps;
     det_reduce_kernel<<<(int)(rblocks < 148 * 32 ? rblocks : 148 * 32), 32 * kReduceWarps, 0, stream>>>(
         grad_out, start, records, grad_value, long_cells, d.D, d.L * d.P, cells, accumulate ? 1 : 0);

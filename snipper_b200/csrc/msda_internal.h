@@ -12,6 +12,10 @@ constexpr int kMaxLevels = 64;
 struct OpDims {
     int N, S, M, D, L, Lq, P;
     int64_t value_batch_stride;  // elements
+    // deterministic grad_value only: batch item b scatters into frame
+    //     (b / frame_q) * frame_slots + min(b % frame_q, frame_local)
+    // of grad_value -- the per-query-frame slots of the fused layer (msda_frames.cu); frame_q == 0: frame b
+    int frame_q = 0, frame_local = 0, frame_slots = 0;
 };
 
 struct SnippetDims {
@@ -83,8 +87,20 @@ cudaError_t launch_backward_deterministic_f32(const float *value, const int64_t 
                                               const OpDims &d, void *workspace, cudaStream_t stream,
                                               bool accumulate);
 
+// grad_value part of the above alone (count / scan / fill / ordered reduce); loc / attn per sample, (N,Lq,M,L,P[,2])
+cudaError_t launch_deterministic_grad_value_f32(const int64_t *shapes, const int64_t *lsi, const float *loc,
+                                                const float *attn, const float *grad_out, float *grad_value,
+                                                const OpDims &d, void *workspace, cudaStream_t stream,
+                                                bool accumulate);
+
 // ---- in-place masked zero-fill (msda_mask.cu) ----
 cudaError_t launch_masked_zero(void *data, const uint8_t *mask, int64_t n, int elem_bytes, cudaStream_t stream);
+
+// ---- layer tail: bias + residual + LayerNorm (+ pos) in one pass (msda_tail.cu) ----
+bool layer_tail_ok(int cols);
+cudaError_t launch_layer_tail(const float *y, const float *bias, const float *residual, const float *gamma,
+                              const float *beta, const float *pos, float *out, float *out_pos, int64_t rows,
+                              int cols, float eps, cudaStream_t stream);
 
 // ---- neighbour-frame pre-summation (msda_frames.cu) ----
 int snippet_num_slots(int T1, int n_frame);
@@ -117,5 +133,15 @@ cudaError_t launch_snippet_backward_f32(const float *value, const int64_t *shape
                                         const float *grad_out, float *grad_value,
                                         float *grad_offsets, float *grad_logits,
                                         const SnippetDims &d, cudaStream_t stream);
+
+// deterministic mode of the fused layer (presummed, fp32): everything but grad_value, no atomics anywhere ...
+cudaError_t launch_snippet_backward_noscatter_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                                  const float *offsets, const float *logits, const float *ref,
+                                                  const float *grad_out, float *grad_offsets, float *grad_logits,
+                                                  const SnippetDims &d, cudaStream_t stream);
+// ... and the per-sample locations / weights the two-pass grad_value needs: loc (N*T1,Lq,M,L,P,2), attn (N*T1,Lq,M,L,P)
+cudaError_t launch_snippet_loc_attn(const int64_t *shapes, const int64_t *lsi, const float *offsets,
+                                    const float *logits, const float *ref, float *loc, float *attn,
+                                    const SnippetDims &d, cudaStream_t stream);
 
 }  // namespace msda

@@ -151,9 +151,9 @@ __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo
     else { lo = 0; hi = T2 - 1; }
 }
 
-// Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each query is
-// done cooperatively through shared memory (one expf per sample), then
-// loc = ref + offset / (W_l, H_l) in the reference's operation order (ms_deform_attn.py:164-165).
+// Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each query (staged in
+// shared memory), then loc = ref + offset / (W_l, H_l) in the reference's operation order
+// (ms_deform_attn.py:164-165).
 // Each sample is parked as ONE 16-byte record {lx, ly, A, off | mask}: A = softmax / k, `off` the
 // byte offset of the (y0,x0) cell (a multiple of 16, so its low four bits carry the corner mask).
 // One LDS.128 per sample and lane in phase 2 instead of an LDS.64 + an LDS.128 -- wide shared loads
@@ -161,57 +161,63 @@ __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo
 // (profiles/r01_run18_*); the row stride comes from the level table once per level, and the four
 // corner weights are recomputed per lane (8 FP instructions, the issue slots are free).
 template <int THREADS, int PAIRS>
-__device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, float *es,
-                                               const LevelTable &lv, const SnipArgs &a, int n, int t1, int q0,
-                                               int m, size_t qbase, const float *__restrict__ offsets,
+__device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, LevelTable &lv, const int64_t *__restrict__ shapes,
+                                               const int64_t *__restrict__ lsi, const SnipArgs &a, int n, int t1,
+                                               int q0, int m, size_t qbase, const float *__restrict__ offsets,
                                                const float *__restrict__ logits,
                                                const float *__restrict__ ref, float inv_k)
 {
     const SnippetDims &d = a.d;
     const int tid = threadIdx.x;
     const int LP = d.L * d.P;
+    // pass 1: EVERY global load of the tile is issued here, back to back -- the level table, the logits, the
+    // offsets and the reference points -- so the CTA waits for one memory round trip, not three in a row
+    // (the projection rows stream from HBM, and with the neighbour-frame loop gone the set-up is ~40 % of a CTA's
+    // life).  Raw {off.x, off.y, ref.u, ref.v} is parked in the record slot until pass 2.
+    load_level_table(lv, shapes, lsi, d.L, d.S);
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
         const int spl = fast_div(i, a.magic_LP);
         const int q = q0 + spl;
         const int lp = i - spl * LP;
         float z = 0.f;
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < d.Lq) {
             z = __ldg(logits + (qbase + q) * d.logit_row_stride + m * LP + lp);
+            const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets + (qbase + q) * d.off_row_stride) + m * LP + lp);
+            const int l = fast_div(lp, a.magic_P);
+            const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+            raw = make_float4(o.x, o.y, __ldg(rp), __ldg(rp + 1));
             if (d.logit_bias != nullptr) z += __ldg(d.logit_bias + m * LP + lp);
+            if (d.off_bias != nullptr) {
+                const float2 b = __ldg(reinterpret_cast<const float2 *>(d.off_bias) + m * LP + lp);
+                raw.x += b.x; raw.y += b.y;
+            }
         }
         zs[i] = z;
+        rec[i + spl] = raw;  // records strided LP + 1 per query
     }
     __syncthreads();
-    for (int i = tid; i < PAIRS * LP; i += THREADS) {
-        const float *z = zs + fast_div(i, a.magic_LP) * LP;
-        float mx = z[0];
-        for (int j = 1; j < LP; ++j) mx = fmaxf(mx, z[j]);
-        es[i] = expf(zs[i] - mx);
-    }
-    __syncthreads();
+    // pass 2: softmax over the query's L*P logits (every thread redoes the L*P exponentials of its query: a few
+    // hundred MUFU ops per CTA, cheaper than a third barrier + a second staging array), then the sample set-up
     for (int i = tid; i < PAIRS * LP; i += THREADS) {
         const int spl = fast_div(i, a.magic_LP);
         const int lp = i - spl * LP;
-        const int q = q0 + spl;
         float4 r = empty_record();  // mask 0: inactive
-        if (q < d.Lq) {
-            const float *e = es + spl * LP;
+        if (q0 + spl < d.Lq) {
+            const float *z = zs + spl * LP;
+            float mx = z[0];
+            for (int j = 1; j < LP; ++j) mx = fmaxf(mx, z[j]);
             float sum = 0.f;
-            for (int j = 0; j < LP; ++j) sum += e[j];
-            const float at = es[i] / sum * inv_k;
+            for (int j = 0; j < LP; ++j) sum += expf(z[j] - mx);
+            const float at = expf(z[lp] - mx) / sum * inv_k;
             const int l = fast_div(lp, a.magic_P);
-            float2 o = __ldg(reinterpret_cast<const float2 *>(offsets + (qbase + q) * d.off_row_stride) + m * LP + lp);
-            if (d.off_bias != nullptr) {
-                const float2 b = __ldg(reinterpret_cast<const float2 *>(d.off_bias) + m * LP + lp);
-                o.x += b.x; o.y += b.y;
-            }
-            const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
-            const float u = __ldg(rp) + o.x / (float)lv.W[l];
-            const float v = __ldg(rp + 1) + o.y / (float)lv.H[l];
+            const float4 raw = rec[i + spl];
+            const float u = raw.z + raw.x / (float)lv.W[l];
+            const float v = raw.w + raw.y / (float)lv.H[l];
             const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
             r = make_record(s, at, a.cell_bytes);
         }
-        rec[i + spl] = r;  // records strided LP + 1 per query
+        rec[i + spl] = r;
     }
     __syncthreads();
 }
@@ -236,7 +242,6 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const int LP = d.L * d.P;
     float4 *rec = reinterpret_cast<float4 *>(smem_raw);
     float *zs = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
-    float *es = zs + Cfg::PAIRS * LP;
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS;
@@ -246,9 +251,7 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const int nf = hi - lo + 1;
     const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;  // first query row of this (n, t1)
 
-    load_level_table(lv, shapes, lsi, d.L, d.S);
-    __syncthreads();
-    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits, ref,
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(rec, zs, lv, shapes, lsi, a, n, t1, q0, m, qbase, offsets, logits, ref,
                                             1.f / (float)nf);
 
     // ---- phase 2: gather from every neighbour frame ----
@@ -287,7 +290,9 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
 }
 
-template <typename VT, int LANES, int PAIRS, int CSB, int MODE>
+// SCATTER == false (presummed only): grad_offsets / grad_logits alone, no atomics anywhere -- the deterministic
+// mode computes grad_value with the two-pass gather of msda_deterministic.cu.
+template <typename VT, int LANES, int PAIRS, int CSB, int MODE, bool SCATTER = true>
 __global__ void __launch_bounds__(SnipCfg<LANES, PAIRS>::THREADS,
                                   MODE == kPresummed ? SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS_PRESUM
                                                      : SnipCfg<LANES, PAIRS>::BWD_MIN_BLOCKS)
@@ -308,8 +313,7 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const int LP = d.L * d.P;
     float4 *frac = reinterpret_cast<float4 *>(smem_raw);  // {lx, ly, A, off | mask}
     float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * Cfg::PAIRS * (LP + 1));
-    float *zs = part;  // phase-1 scratch aliases `part` ([rec][SUBS][3] >= 2 floats per record)
-    float *es = part + Cfg::PAIRS * LP;
+    float *zs = part;  // phase-1 scratch aliases `part` ([rec][SUBS][3] >= 1 float per record)
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * Cfg::PAIRS;
@@ -319,9 +323,7 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const int nf = hi - lo + 1;
     const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;
 
-    load_level_table(lv, shapes, lsi, d.L, d.S);
-    __syncthreads();
-    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(frac, zs, es, lv, a, n, t1, q0, m, qbase, offsets, logits, ref,
+    snippet_phase1<Cfg::THREADS, Cfg::PAIRS>(frac, zs, lv, shapes, lsi, a, n, t1, q0, m, qbase, offsets, logits, ref,
                                             1.f / (float)nf);
 
     // ---- phase 2: every thread participates (full-mask shuffles) ----
@@ -361,7 +363,7 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
             // (the backward, unlike the forward, prefers loads in flight over occupancy: not unrolling
             //  this loop -- 64 registers, 5 CTAs per SM -- measured 4-7 % slower, profiles/r01_run24_*)
             if (MODE == kPresummed) {
-                gather_scatter<VT, CSB, true>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
+                gather_scatter<VT, CSB, SCATTER>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
             } else if (MODE == kDirect) {
                 for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride)
                     gather_scatter<VT, CSB, true>(mt, bw, g, gr, p0, gp0, a.cell_bytes, pa, px, py);
@@ -462,7 +464,7 @@ static cudaError_t launch_snip_fwd(const typename Chunk<VT>::elem *value, const 
     using Cfg = SnipCfg<LANES, PAIRS>;
     const SnipArgs a = make_snip_args<VT>(d);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + 2 * sizeof(float) * Cfg::PAIRS * d.L * d.P;
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + sizeof(float) * Cfg::PAIRS * d.L * d.P;
     constexpr int C = snip_csb<VT, LANES>();
     const bool imm = C != 0 && d.M * d.D == 384;
 #define MSDA_LAUNCH_FWD(CSB_, MODE_)                                                                   \
@@ -519,6 +521,67 @@ static cudaError_t launch_snip_bwd(const typename Chunk<VT>::elem *value, const 
 #undef MSDA_LAUNCH_BWD
 }
 
+template <typename VT, int LANES, int PAIRS>
+static cudaError_t launch_snip_bwd_noscatter(const typename Chunk<VT>::elem *value, const int64_t *shapes,
+                                             const int64_t *lsi, const float *offsets, const float *logits,
+                                             const float *ref, const typename Chunk<VT>::elem *grad_out,
+                                             float *grad_offsets, float *grad_logits, const SnippetDims &d,
+                                             cudaStream_t stream)
+{
+    using Cfg = SnipCfg<LANES, PAIRS>;
+    const SnipArgs a = make_snip_args<VT>(d);
+    const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
+    const size_t smem = sizeof(float4) * Cfg::PAIRS * (d.L * d.P + 1) + sizeof(float) * 3 * Cfg::SUBS * Cfg::PAIRS * d.L * d.P;
+    auto kernel = msda_snippet_bwd_kernel<VT, LANES, PAIRS, 0, kPresummed, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, Cfg::THREADS, smem, stream>>>(value, shapes, lsi, offsets, logits, ref, grad_out, nullptr,
+                                                grad_offsets, grad_logits, a);
+    return cudaGetLastError();
+}
+
+// Per-sample sampling locations and attention weights written out (deterministic mode only: the two-pass
+// grad_value of msda_deterministic.cu consumes the per-call layout).  One thread per (n,t1,q,m); same
+// operation order as snippet_phase1, so floor() picks the cells the forward gathered.
+__global__ void __launch_bounds__(128)
+snippet_loc_attn_kernel(const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+                        const float *__restrict__ offsets, const float *__restrict__ logits,
+                        const float *__restrict__ ref, float *__restrict__ loc, float *__restrict__ attn,
+                        const SnippetDims d, int64_t total)
+{
+    __shared__ LevelTable lv;
+    load_level_table(lv, shapes, lsi, d.L, d.S);
+    __syncthreads();
+    const int LP = d.L * d.P;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i % d.M);
+        const int64_t row = i / d.M;                       // (n*T1 + t1)*Lq + q
+        const int q = (int)(row % d.Lq);
+        const int64_t nt = row / d.Lq;
+        const int t1 = (int)(nt % d.T1), n = (int)(nt / d.T1);
+        int lo, hi;
+        frame_range(t1, d.n_frame, d.T2, lo, hi);
+        const float inv_k = 1.f / (float)(hi - lo + 1);
+        const float *zrow = logits + row * d.logit_row_stride + m * LP;
+        const float *zb = d.logit_bias ? d.logit_bias + m * LP : nullptr;
+        float mx = -INFINITY;
+        for (int j = 0; j < LP; ++j) mx = fmaxf(mx, __ldg(zrow + j) + (zb ? __ldg(zb + j) : 0.f));
+        float sum = 0.f;
+        for (int j = 0; j < LP; ++j) sum += expf(__ldg(zrow + j) + (zb ? __ldg(zb + j) : 0.f) - mx);
+        const float2 *orow = reinterpret_cast<const float2 *>(offsets + row * d.off_row_stride) + m * LP;
+        const float2 *ob = d.off_bias ? reinterpret_cast<const float2 *>(d.off_bias) + m * LP : nullptr;
+        for (int j = 0; j < LP; ++j) {
+            const int l = j / d.P;
+            float2 o = __ldg(orow + j);
+            if (ob) { const float2 b = __ldg(ob + j); o.x += b.x; o.y += b.y; }
+            const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+            const int64_t si = i * LP + j;
+            loc[2 * si] = __ldg(rp) + o.x / (float)lv.W[l];
+            loc[2 * si + 1] = __ldg(rp + 1) + o.y / (float)lv.H[l];
+            attn[si] = expf(__ldg(zrow + j) + (zb ? __ldg(zb + j) : 0.f) - mx) / sum * inv_k;
+        }
+    }
+}
+
 #define MSDA_DISPATCH_LANES(D, CALL)                                  \
     switch ((D) / 4) {                                                \
         case 4: return CALL(float, 4, 16);                            \
@@ -569,6 +632,30 @@ cudaError_t launch_snippet_backward_f32(const float *value, const int64_t *shape
     launch_snip_bwd<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_value, grad_offsets, grad_logits, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
+}
+
+cudaError_t launch_snippet_backward_noscatter_f32(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                                  const float *offsets, const float *logits, const float *ref,
+                                                  const float *grad_out, float *grad_offsets, float *grad_logits,
+                                                  const SnippetDims &d, cudaStream_t stream)
+{
+    if (!d.presummed) return cudaErrorInvalidValue;
+#define CALL(VT, LN, PR) \
+    launch_snip_bwd_noscatter<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, grad_out, grad_offsets, grad_logits, d, stream)
+    MSDA_DISPATCH_LANES(d.D, CALL)
+#undef CALL
+}
+
+cudaError_t launch_snippet_loc_attn(const int64_t *shapes, const int64_t *lsi, const float *offsets,
+                                    const float *logits, const float *ref, float *loc, float *attn,
+                                    const SnippetDims &d, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)d.N * d.T1 * d.Lq * d.M;
+    if (total == 0) return cudaSuccess;
+    const int64_t blocks = (total + 127) / 128;
+    snippet_loc_attn_kernel<<<(int)(blocks < 148 * 32 ? blocks : 148 * 32), 128, 0, stream>>>(shapes, lsi, offsets, logits,
+                                                                                           ref, loc, attn, d, total);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_snippet_forward_bf16(const void *value_, const int64_t *shapes,

@@ -180,6 +180,18 @@ class MSDeformAttn(nn.Module):
         per-pixel (N,T2,S[,1]) mask, which the kernels then read as one byte per pixel.
         Returns (N,T1,Lq,C), plus ``(sampling_locations per t1, attention_weights per t1)`` when
         ``attention_vis``."""
+        out, vis = self._attend(query, reference_points, input_flatten, input_spatial_shapes,
+                                input_level_start_index, input_padding_mask)
+        out = self.output_proj(out)
+        if self.attention_vis:
+            return out, vis
+        return out
+
+    def _attend(self, query, reference_points, input_flatten, input_spatial_shapes,
+                input_level_start_index, input_padding_mask=None):
+        """Everything of ``forward`` up to (not including) ``output_proj``: (N,T1,Lq,C) attention output and the
+        visualisation payload (None unless ``attention_vis``).  The fused layer tails (snipper_b200/layers.py)
+        apply ``output_proj`` themselves so that its bias folds into the residual + LayerNorm pass."""
         N, T1, Lq, _ = query.shape
         _, T2, S, _ = input_flatten.shape
         M, L, P = self.n_heads, self.n_levels, self.n_points
@@ -217,10 +229,7 @@ class MSDeformAttn(nn.Module):
             value = value.view(N, T2, S, M, self.d_model // M)
             out, vis = self._forward_per_call(query, reference_points, value, input_spatial_shapes,
                                               input_level_start_index)
-        out = self.output_proj(out)
-        if self.attention_vis:
-            return out, vis
-        return out
+        return out, vis
 
     # -------------------------------------------------------------------------------------
     def _vis_fused(self, offsets, logits, reference_points, spatial_shapes, T2):

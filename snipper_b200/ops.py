@@ -183,13 +183,15 @@ def msda_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tens
             ws_bytes = capi.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dt, flags)
             ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=value.device)
         ws_ptr = 0 if ws is None else (ws.data_ptr() + 255) // 256 * 256
-        STATS.launches += 1
-        st = capi.lib().msda_backward(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
-            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
-            N, S, M, D, L, Lq, P, vbs, int(im2col_step), dt, flags, ws_ptr, ws_bytes,
-            _stream(value.device))
+        # deterministic: no-scatter kernel, memset, count, 3 scan kernels, fill, reduce, long-list reduce
+        with _Launch("msda_backward_deterministic" if deterministic else "msda_backward", (N, S, M, D, L, Lq, P),
+                     value.device, 9 if deterministic else 2):
+            st = capi.lib().msda_backward(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+                grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+                N, S, M, D, L, Lq, P, vbs, int(im2col_step), dt, flags, ws_ptr, ws_bytes,
+                _stream(value.device))
     capi.check(st, "ms_deform_attn_backward", N, im2col_step)
     if bf16:
         grad_value = grad_value.to(torch.bfloat16)
@@ -345,7 +347,7 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(),
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, 0, 0,
-            _DTYPES[value.dtype], 0, _stream(value.device))
+            _DTYPES[value.dtype], 0, None, 0, _stream(value.device))
     capi.check(status, "msda_snippet_backward")
     if value.dtype != torch.float32:
         grad_value = grad_value.to(value.dtype)
@@ -532,18 +534,26 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
     grad_proj = torch.empty_like(proj)
     dims = (N, T2, T1, S, M, D, L, Lq, P)
     L_ = capi.lib()
-    if deterministic:
-        raise RuntimeError("deterministic fused backward: not built yet")
+    if deterministic and not (presum and dt == torch.float32):
+        raise RuntimeError("the deterministic fused backward runs on the pre-summed float32 path")
     if presum:
         slots = value_or_vsum.shape[1]
         gsum = torch.empty((N, slots, S, M, D), dtype=torch.float32, device=dev)   # fp32 accumulation
-        with torch.cuda.device(dev), _Launch("snippet_backward_presummed", dims, dev, 2):
+        flags, ws_ptr, ws_bytes, ws, tag, n_kernels = capi.MSDA_FLAG_PRESUMMED, None, 0, None, "snippet_backward_presummed", 2
+        if deterministic:
+            # bit-reproducible: no-scatter kernel + two-pass ordered grad_value over the slots (include/msda_b200.h)
+            flags |= capi.MSDA_FLAG_DETERMINISTIC
+            ws_bytes = L_.msda_snippet_backward_workspace_bytes(N, T1, int(n_frame), S, M, D, L, Lq, P, _DTYPES[dt], flags)
+            ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            tag, n_kernels = "snippet_backward_deterministic", 10
+        with torch.cuda.device(dev), _Launch(tag, dims, dev, n_kernels):
             status = L_.msda_snippet_backward(
                 value_or_vsum.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                 proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
                 gsum.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
                 N, T2, T1, int(n_frame), S, M, D, L, Lq, P, 0, 0, rsn, rst, 3 * mlp, 3 * mlp,
-                _ptr(offsets_bias), _ptr(logits_bias), None, 0, 0, _DTYPES[dt], capi.MSDA_FLAG_PRESUMMED, _stream(dev))
+                _ptr(offsets_bias), _ptr(logits_bias), None, 0, 0, _DTYPES[dt], flags, ws_ptr, ws_bytes, _stream(dev))
         capi.check(status, "msda_snippet_backward")
         grad_value = torch.empty((N, T2, S, M, D), dtype=dt, device=dev)
         with torch.cuda.device(dev), _Launch("frame_unsum", (N, T2, T1, S, M * D), dev):
@@ -559,7 +569,7 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
             proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
-            _ptr(offsets_bias), _ptr(logits_bias), _ptr(mask), mrs, mcs, _DTYPES[dt], 0, _stream(dev))
+            _ptr(offsets_bias), _ptr(logits_bias), _ptr(mask), mrs, mcs, _DTYPES[dt], 0, None, 0, _stream(dev))
     capi.check(status, "msda_snippet_backward")
     if dt != torch.float32:
         grad_value = grad_value.to(dt)
@@ -627,3 +637,49 @@ def snippet_attention(value: Tensor, value_mask: Optional[Tensor], spatial_shape
     out, _ = torch.ops.snipper_b200.snippet_attn(value, value_mask, spatial_shapes, level_start_index, proj,
                                                  offsets_bias, logits_bias, reference_points, n_frame, bool(presum))
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# layer tail: bias + residual + LayerNorm (+ pos) in one pass
+# ------------------------------------------------------------------------------------------
+def layer_tail_supported(y: Tensor, residual: Tensor) -> bool:
+    """fp32 CUDA rows of 128*k <= 1024 channels, inference (no autograd formula exists for this op)."""
+    C = y.shape[-1]
+    return (y.is_cuda and y.dtype == torch.float32 and residual.dtype == torch.float32 and C % 128 == 0 and C <= 1024
+            and y.shape == residual.shape and not (torch.is_grad_enabled() and (y.requires_grad or residual.requires_grad)))
+
+
+@torch.library.custom_op("snipper_b200::layer_tail", mutates_args=())
+def layer_tail(y: Tensor, bias: Optional[Tensor], residual: Tensor, gamma: Tensor, beta: Tensor,
+               pos: Optional[Tensor], eps: float) -> Tuple[Tensor, Tensor]:
+    """(LayerNorm(residual + y + bias), that + pos) -- the second tensor is empty when ``pos`` is None.
+    Reference: deformable_transformer.py:204-205 / :194-198 / :294-295 and with_pos_embed :188-190."""
+    _require_cuda(y, "y")
+    C = y.shape[-1]
+    if y.dtype != torch.float32 or C % 128 != 0 or C > 1024 or residual.shape != y.shape:
+        raise RuntimeError("layer_tail: float32 rows of 128*k <= 1024 channels, residual shaped like y")
+    y, residual = y.contiguous(), residual.contiguous()
+    for t, n in ((bias, C), (gamma, C), (beta, C)):
+        if t is not None and (t.numel() != n or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("layer_tail: bias / gamma / beta must be contiguous float32 vectors of C elements")
+    rows = y.numel() // C
+    out = torch.empty_like(y)
+    if pos is not None:
+        if pos.shape != y.shape or pos.dtype != torch.float32:
+            raise RuntimeError("layer_tail: pos must be shaped like y")
+        pos = pos.contiguous()
+        out_pos = torch.empty_like(y)
+    else:
+        out_pos = y.new_empty((0,))
+    with torch.cuda.device(y.device), _Launch("layer_tail", (rows, C, int(pos is not None)), y.device):
+        status = capi.lib().msda_layer_tail(y.data_ptr(), _ptr(bias), residual.data_ptr(), gamma.data_ptr(),
+                                            beta.data_ptr(), _ptr(pos), out.data_ptr(),
+                                            out_pos.data_ptr() if pos is not None else None, rows, C, float(eps),
+                                            capi.MSDA_DTYPE_F32, _stream(y.device))
+    capi.check(status, "msda_layer_tail")
+    return out, out_pos
+
+
+@layer_tail.register_fake
+def _(y, bias, residual, gamma, beta, pos, eps):
+    return torch.empty_like(y), (torch.empty_like(y) if pos is not None else y.new_empty((0,)))

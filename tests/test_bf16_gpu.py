@@ -123,7 +123,11 @@ def test_module_under_autocast_uses_bf16_kernels():
     refp = torch.rand(1, 4, S, 3, 2, device=dev)
     want = mod(q, refp, src, shapes, lsi)
     ops.STATS.reset()
+    ops.STATS.timing = True
     with torch.autocast("cuda", dtype=torch.bfloat16):
         got = mod(q, refp, src, shapes, lsi)
-    assert ops.STATS.launches == 1
+    ops.STATS.timing = False
+    # encoder-sized query set: one streaming pass that sums the neighbour frames + one gather launch, nothing else
+    assert ops.STATS.launches == 2
+    assert sorted(tag for tag, _, _, _ in ops.STATS.events) == ["frame_sum", "snippet_forward_presummed"]
     assert rel_err(got.float(), want) < 3e-2   # bf16 GEMMs on both sides of the op dominate this error

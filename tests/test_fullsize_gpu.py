@@ -185,3 +185,76 @@ def test_presummed_value_is_the_masked_neighbour_sum():
     want_gv = torch.stack([gsum[:, 0] + gsum[:, 1], gsum[:, 0] + gsum[:, 1], gsum[:, 1],
                            torch.zeros_like(gsum[:, 0]), torch.zeros_like(gsum[:, 0])], 1)
     assert rel_err(gv, want_gv) < 1e-6
+
+
+# ------------------------------------------------------------------- deterministic mode of the fused layer
+def _ours_deterministic(c, n_frame):
+    import snipper_b200
+    snipper_b200.set_deterministic(True)
+    try:
+        return _ours(c, n_frame, torch.float32, None, True)      # presum=None: the deterministic mode picks the slots
+    finally:
+        snipper_b200.set_deterministic(False)
+
+
+def test_encoder_layer_full_size_deterministic_backward():
+    """north_star: 'offers a deterministic two-pass mode' -- for the kernel training actually runs: bit-identical
+    run to run at the full bench size, and equal to the oracle."""
+    S = sum(h * w for h, w in LEVELS)
+    c = _case(1, 4, 4, S, seed=11, encoder=True)
+    a = _ours_deterministic(c, 4)
+    b = _ours_deterministic(c, 4)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    _compare(a, _oracle(c, 4, torch.float32), torch.float32, c["pix"])
+
+
+def test_decoder_layer_deterministic_backward_shares_the_all_frames_slot():
+    """T1 = 4 + 2: both future query frames scatter into ONE slot; the ordered reduction merges them canonically."""
+    c = _case(2, 6, 4, 60, seed=34, encoder=False, sigma_px=6.0)
+    a = _ours_deterministic(c, 4)
+    b = _ours_deterministic(c, 4)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    _compare(a, _oracle(c, 4, torch.float32), torch.float32, c["pix"])
+
+
+def test_module_deterministic_mode_stays_on_the_fused_path():
+    import snipper_b200
+    from snipper_b200 import ops
+    torch.manual_seed(2)
+    shapes = torch.as_tensor([(19, 25), (10, 13), (5, 7)], dtype=torch.long, device=DEV)
+    lsi = level_start_index(shapes.cpu()).to(DEV)
+    S = int(shapes.prod(1).sum())
+    mod = snipper_b200.MSDeformAttn(384, 3, 8, 4, 4, "encoder").to(DEV)
+    with torch.no_grad():
+        mod.sampling_offsets[0].weight.normal_(0, 0.05)
+        mod.attention_weights[0].weight.normal_(0, 0.2)
+    q = torch.randn(2, 4, S, 384, device=DEV)
+    src = torch.randn(2, 4, S, 384, device=DEV)
+    refp = torch.rand(2, 4, S, 3, 2, device=DEV)
+    pad = torch.rand(2, 4, S, 1, device=DEV) < 0.1
+
+    def run():
+        for p in mod.parameters():
+            p.grad = None
+        a, b = q.clone().requires_grad_(True), src.clone().requires_grad_(True)
+        ops.STATS.reset()
+        ops.STATS.timing = True
+        mod(a, refp, b, shapes, lsi, pad.expand(2, 4, S, 384)).square().sum().backward()
+        ops.STATS.timing = False
+        return [a.grad, b.grad] + [p.grad.clone() for p in mod.parameters()], sorted({e[0] for e in ops.STATS.events})
+
+    want, tags0 = run()
+    snipper_b200.set_deterministic(True)
+    try:
+        g1, tags = run()
+        g2, _ = run()
+    finally:
+        snipper_b200.set_deterministic(False)
+    assert tags == ["frame_sum", "frame_unsum", "snippet_backward_deterministic", "snippet_forward_presummed"], tags
+    assert "snippet_backward_presummed" in tags0
+    for x, y in zip(g1, g2):
+        assert torch.equal(x, y)                       # bit-identical run to run
+    for x, y in zip(g1, want):
+        assert rel_err(x, y) < 1e-4                    # and the same gradients as the atomic path

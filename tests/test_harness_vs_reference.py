@@ -41,3 +41,42 @@ def test_harness_matches_reference_model(num_future):
             assert rel_err(a[k], b[k]) < 1e-5
     assert rel_err(g_refs, w_refs) < 1e-5
     assert len(g_att) == len(w_att)
+
+
+def test_drop_in_surfaces_rebind_the_unmodified_reference():
+    """install_module() makes the reference's own build_model construct the fused class (surface 3) with the
+    reference's state-dict layout; install_extension_shim() rebinds the name the reference's
+    MSDeformAttnFunction resolves at call time (surface 1, ms_deform_attn_func.py:28,38)."""
+    import sys
+    import snipper_b200
+    kw = dict(hidden_dim=96, num_frames=2, num_future_frames=1, enc_layers=2, dec_layers=3, num_queries=5,
+              dim_feedforward=64, use_pytorch_deform=0)
+    ref_model, _ = ref_loader.build_reference_model(**kw)
+    import models.deformable_transformer as dt
+    import models.ops.modules as ref_modules
+    ref_cls = ref_modules.MSDeformAttn
+    assert sum(isinstance(m, ref_cls) for m in ref_model.modules()) == 2 + 3
+    try:
+        snipper_b200.install_module()
+        assert dt.MSDeformAttn is snipper_b200.MSDeformAttn
+        ours, _ = ref_loader.build_reference_model(**kw)
+        mods = [m for m in ours.modules() if isinstance(m, snipper_b200.MSDeformAttn)]
+        assert len(mods) == 2 + 3 and not any(isinstance(m, ref_cls) for m in ours.modules())
+        assert [m.mode for m in mods] == ["encoder"] * 2 + ["decoder"] * 3
+        assert [m.attention_vis for m in mods] == [False] * 2 + [True] * 3
+        assert all(m.n_frame == 2 and m.d_model == 96 for m in mods)
+        # DeformableTransformer._reset_parameters type-tests the class (deformable_transformer.py:62-64): ours was re-initialised
+        assert all(float(m.sampling_offsets[0].weight.abs().max()) == 0.0 for m in mods)
+        missing, unexpected = ours.load_state_dict(ref_model.state_dict(), strict=True)   # same keys, aliased slots included
+        assert not missing and not unexpected
+    finally:
+        for name in ("models.ops.modules", "models.ops.modules.ms_deform_attn", "models.deformable_transformer"):
+            sys.modules[name].MSDeformAttn = ref_cls
+    import models.ops.functions.ms_deform_attn_func as ref_func
+    before = getattr(ref_func, "MSDA", None)
+    try:
+        shim = snipper_b200.install_extension_shim()
+        assert ref_func.MSDA is shim and hasattr(shim, "ms_deform_attn_forward") and hasattr(shim, "ms_deform_attn_backward")
+    finally:
+        if before is not None:
+            ref_func.MSDA = before

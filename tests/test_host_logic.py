@@ -71,11 +71,18 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert fwd(N=0, mask=256, mrs=384, mcs=1, flags=capi.MSDA_FLAG_PRESUMMED) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert fwd(N=0, flags=capi.MSDA_FLAG_PRESUMMED) == capi.MSDA_OK
     assert fwd(N=0, flags=64) == capi.MSDA_ERR_INVALID_ARGUMENT
-    # the fused layer's deterministic mode is composed by the host from msda_frame_sum + msda_backward(DETERMINISTIC):
-    # the fused entry point itself rejects the flag as an invalid argument (not as a dtype problem)
-    assert L.msda_snippet_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 4, 4, 4, 100, 8, 48, 3, 10, 4,
-                                   0, 0, 0, 0, 0, 0, None, None, None, 0, 0, F32, capi.MSDA_FLAG_DETERMINISTIC, 0) \
-        == capi.MSDA_ERR_INVALID_ARGUMENT
+    # deterministic mode of the fused layer: pre-summed float32 only, needs its workspace
+    def bwd(flags, dtype=F32, ws=None, ws_bytes=0):
+        return L.msda_snippet_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 4, 4, 4, 100, 8, 48, 3, 10, 4,
+                                       0, 0, 0, 0, 0, 0, None, None, None, 0, 0, dtype, flags, ws, ws_bytes, 0)
+    DET, PRE = capi.MSDA_FLAG_DETERMINISTIC, capi.MSDA_FLAG_PRESUMMED
+    assert bwd(DET) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert bwd(DET | PRE, dtype=BF16) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert bwd(DET | PRE) == capi.MSDA_ERR_WORKSPACE
+    need = L.msda_snippet_backward_workspace_bytes(1, 4, 4, 100, 8, 48, 3, 10, 4, F32, DET | PRE)
+    assert need > 0 and L.msda_snippet_backward_workspace_bytes(1, 4, 4, 100, 8, 48, 3, 10, 4, F32, PRE) == 0
+    assert bwd(DET | PRE, ws=256, ws_bytes=need - 1) == capi.MSDA_ERR_WORKSPACE
+    assert bwd(DET | PRE, ws=257, ws_bytes=need) == capi.MSDA_ERR_WORKSPACE
     # neighbour-frame pre-summation: slot structure, strategy choice, validation
     assert L.msda_snippet_num_slots(4, 4) == 4 and L.msda_snippet_num_slots(6, 4) == 5 and L.msda_snippet_num_slots(2, 4) == 2
     assert L.msda_snippet_prefers_presum(4, 4, 4, 9875, 3, 9875, 4) == 1     # encoder: 10 frame pairs -> 4 gathers

@@ -201,7 +201,7 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
         r = L.msda_snippet_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, 0, st)
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, 0, None, 0, st)
         assert r == 0, r
 
     # neighbour-frame pre-summation: streaming pass + one gather per query frame (and the mirror in the backward)
@@ -228,11 +228,24 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
         r = L.msda_snippet_backward(vsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gsum.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, PRE, st)
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, PRE, None, 0, st)
         assert r == 0, r
 
     def funsum():
         r = L.msda_frame_unsum(gsum.data_ptr(), pix.data_ptr(), gv2.data_ptr(), N, T2, T1, n_frame, S, M * D, 1, 0, dt, st)
+        assert r == 0, r
+
+    DET = PRE | capi.MSDA_FLAG_DETERMINISTIC
+    ws_bytes = 0 if bf16 else L.msda_snippet_backward_workspace_bytes(N, T1, n_frame, S, M, D, Lv, Lq, P, dt, DET)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    keep = keep + (ws,)
+
+    def bwd_pre_det():
+        r = L.msda_snippet_backward(vsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                    logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gsum.data_ptr(),
+                                    goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, DET, ws_ptr, ws_bytes, st)
         assert r == 0, r
 
     def layer_fwd_pre():
@@ -253,6 +266,8 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
              "layer_fwd_presummed(sum+gather)": (layer_fwd_pre, fwd_b),
              "bwd_presummed": (bwd_pre, bwd_b), "frame_unsum": (funsum, full * (4 * slots + e * T2)),
              "layer_bwd_presummed(scatter+unsum)": (layer_bwd_pre, bwd_b)}
+    if not bf16:
+        extra["bwd_presummed_deterministic"] = (bwd_pre_det, bwd_b)
     return fwd, bwd, fwd_b, bwd_b, keep, extra
 
 
