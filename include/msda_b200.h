@@ -141,7 +141,12 @@ MSDA_API int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_e
  *   offsets_bias     (M,L,P,2) or NULL  biases of the two Linear layers, added in-kernel (saves the GEMM
  *   logits_bias      (M,L,P)   or NULL  epilogue pass over the projection output)
  *   reference_points (N,T1,Lq,L,2)      element strides ref_stride_n / ref_stride_t (0 allowed:
- *                                       the encoder expands one frame over T1)
+ *                                       the encoder expands one frame over T1); may be NULL with:
+ *   encoder_valid_ratios (N,L,2) or NULL  encoder self-attention (Lq == S: query q is pixel q of the pyramid): the
+ *                                       reference points are computed in-kernel from the query index and these
+ *                                       (w,h) valid ratios, bit-identical to get_reference_points
+ *                                       (models/deformable_transformer.py:219-232), instead of being materialised
+ *                                       once per forward and re-read by every layer
  *   value_mask       NULL, or the padding mask over value (N,T2,S,M*D) (layout: see Conventions): masked
  *                                       elements are gathered as zero and receive no gradient -- the
  *                                       reference's value.masked_fill(mask, 0) (ms_deform_attn.py:116-117)
@@ -165,7 +170,7 @@ MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shap
                          int64_t value_stride_n, int64_t value_stride_t,
                          int64_t ref_stride_n, int64_t ref_stride_t,
                          int64_t offsets_row_stride, int64_t logits_row_stride,
-                         const void *offsets_bias, const void *logits_bias,
+                         const void *offsets_bias, const void *logits_bias, const void *encoder_valid_ratios,
                          const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                          int dtype, unsigned flags, void *stream);
 
@@ -190,7 +195,7 @@ MSDA_API int msda_snippet_backward(const void *value, const int64_t *spatial_sha
                           int64_t value_stride_n, int64_t value_stride_t,
                           int64_t ref_stride_n, int64_t ref_stride_t,
                           int64_t offsets_row_stride, int64_t logits_row_stride,
-                          const void *offsets_bias, const void *logits_bias,
+                          const void *offsets_bias, const void *logits_bias, const void *encoder_valid_ratios,
                           const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                           int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream);
 

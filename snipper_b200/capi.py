@@ -70,9 +70,9 @@ def lib():
     L.msda_masked_zero.restype = i32
     L.msda_masked_zero.argtypes = [vp, vp, i64, i32, vp]
     L.msda_snippet_forward.restype = i32
-    L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp]
+    L.msda_snippet_forward.argtypes = [vp] * 7 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, vp, i64, i32, i32, u32, vp]
     L.msda_snippet_backward.restype = i32
-    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, i64, i32, i32, u32, vp, sz, vp]
+    L.msda_snippet_backward.argtypes = [vp] * 10 + [i32] * 10 + [i64] * 6 + [vp, vp, vp, vp, i64, i32, i32, u32, vp, sz, vp]
     L.msda_snippet_backward_workspace_bytes.restype = sz
     L.msda_snippet_backward_workspace_bytes.argtypes = [i32] * 10 + [u32]
     L.msda_snippet_num_slots.restype = i32

@@ -218,6 +218,7 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
                         int num_query, int num_point, int64_t value_stride_n, int64_t value_stride_t,
                         int64_t ref_stride_n, int64_t ref_stride_t, int64_t offsets_row_stride,
                         int64_t logits_row_stride, const void *offsets_bias, const void *logits_bias,
+                        const void *encoder_valid_ratios,
                         const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                         int dtype, unsigned flags)
 {
@@ -244,7 +245,10 @@ static int snippet_dims(msda::SnippetDims &d, int batch, int n_src_frames, int n
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
                           static_cast<const float *>(offsets_bias), static_cast<const float *>(logits_bias),
+                          static_cast<const float *>(encoder_valid_ratios),
                           presummed ? 1 : 0, value_mask, mask_row_stride, mask_col_stride};
+    // analytic reference points: the queries ARE the pixels of the pyramid
+    if (encoder_valid_ratios != nullptr && num_query != spatial_size) return MSDA_ERR_INVALID_ARGUMENT;
     if (!msda::snippet_ok(d, dtype == MSDA_DTYPE_BF16 ? 2 : 4)) return MSDA_ERR_INVALID_ARGUMENT;
     return MSDA_OK;
 }
@@ -269,7 +273,7 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
                          int64_t value_stride_n, int64_t value_stride_t,
                          int64_t ref_stride_n, int64_t ref_stride_t,
                          int64_t offsets_row_stride, int64_t logits_row_stride,
-                         const void *offsets_bias, const void *logits_bias,
+                         const void *offsets_bias, const void *logits_bias, const void *encoder_valid_ratios,
                          const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                          int dtype, unsigned flags, void *stream)
 {
@@ -278,10 +282,12 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
-                          offsets_bias, logits_bias, value_mask, mask_row_stride, mask_col_stride, dtype, flags);
+                          offsets_bias, logits_bias, encoder_valid_ratios, value_mask, mask_row_stride, mask_col_stride,
+                          dtype, flags);
     if (st != MSDA_OK) return st;
     if (batch == 0 || num_query == 0) return MSDA_OK;
-    if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !reference_points || !output)
+    if (!value || !spatial_shapes || !level_start_index || !offsets || !logits ||
+        (!reference_points && !encoder_valid_ratios) || !output)
         return MSDA_ERR_INVALID_ARGUMENT;
     if (!aligned16(value) || !aligned16(output) || (reinterpret_cast<uintptr_t>(offsets) & 7u) ||
         (reinterpret_cast<uintptr_t>(logits) & 3u) || (reinterpret_cast<uintptr_t>(offsets_bias) & 7u))
@@ -306,7 +312,7 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           int64_t value_stride_n, int64_t value_stride_t,
                           int64_t ref_stride_n, int64_t ref_stride_t,
                           int64_t offsets_row_stride, int64_t logits_row_stride,
-                          const void *offsets_bias, const void *logits_bias,
+                          const void *offsets_bias, const void *logits_bias, const void *encoder_valid_ratios,
                           const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                           int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream)
 {
@@ -319,8 +325,10 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
                           value_stride_t, ref_stride_n, ref_stride_t, offsets_row_stride, logits_row_stride,
-                          offsets_bias, logits_bias, value_mask, mask_row_stride, mask_col_stride, dtype, flags);
+                          offsets_bias, logits_bias, encoder_valid_ratios, value_mask, mask_row_stride, mask_col_stride,
+                          dtype, flags);
     if (st != MSDA_OK) return st;
+    if (!reference_points && encoder_valid_ratios) reference_points = encoder_valid_ratios;  // never dereferenced; passes the null checks
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int gframes = (flags & MSDA_FLAG_PRESUMMED) ? msda::snippet_num_slots(n_query_frames, n_frame) : n_src_frames;
     const size_t value_elems = (size_t)batch * gframes * spatial_size * num_heads * channels;

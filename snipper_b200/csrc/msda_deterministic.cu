@@ -197,10 +197,10 @@ __device__ __forceinline__ void rank_sort(const ListSmem &l, int cnt, int tid, i
 
 // Ordered sum of one cell by one warp.  Returns through `dst` (global).
 __device__ __forceinline__ void ordered_sum_warp(const ListSmem &l, int cnt, const float *__restrict__ grad_out,
-                                                 float *__restrict__ dst, int D, int lane, bool accumulate)
+                                                 float *__restrict__ dst, int D, int lane, bool accumulate, bool vec)
 {
     const int q4 = D >> 2;
-    if ((D & 3) == 0 && q4 <= 16) {
+    if (vec && (D & 3) == 0 && q4 <= 16) {  // vec: grad_out and grad_value are 16-byte aligned
         // two interleaved partial sums: lanes [0,q4) take even list positions, [q4,2*q4) odd ones
         const int half = lane / q4, c4 = lane - half * q4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(32 * kReduceWarps)
 det_reduce_kernel(const float *__restrict__ grad_out, const int *__restrict__ start,
                   const CornerRec *__restrict__ records, float *__restrict__ grad_value,
                   int *__restrict__ long_cells /* [0] = count, then cell indices */,
-                  int D, int LP, int64_t cells, int accumulate)
+                  int D, int LP, int64_t cells, int accumulate, int vec)
 {
     __shared__ int s_id[kReduceWarps][kWarpList];
     __shared__ int s_row[kReduceWarps][kWarpList];
@@ -269,7 +269,7 @@ det_reduce_kernel(const float *__restrict__ grad_out, const int *__restrict__ st
         __syncwarp();
         rank_sort(l, cnt, lane, 32);
         __syncwarp();
-        ordered_sum_warp(l, cnt, grad_out, dst, D, lane, accumulate != 0);
+        ordered_sum_warp(l, cnt, grad_out, dst, D, lane, accumulate != 0, vec != 0);
         __syncwarp();
     }
 }
@@ -277,7 +277,7 @@ det_reduce_kernel(const float *__restrict__ grad_out, const int *__restrict__ st
 __global__ void __launch_bounds__(kLongThreads)
 det_reduce_long_kernel(const float *__restrict__ grad_out, const int *__restrict__ start,
                        const CornerRec *__restrict__ records, float *__restrict__ grad_value,
-                       const int *__restrict__ long_cells, int D, int LP, int accumulate)
+                       const int *__restrict__ long_cells, int D, int LP, int accumulate, int vec)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     ListSmem l;
@@ -304,7 +304,7 @@ det_reduce_long_kernel(const float *__restrict__ grad_out, const int *__restrict
             rank_sort(l, cnt, tid, kLongThreads);
             __syncthreads();
             // the ordered sum itself is one warp's job (fixed reduction shape, same as the short path)
-            if (wid == 0) ordered_sum_warp(l, cnt, grad_out, dst, D, lane, accumulate != 0);
+            if (wid == 0) ordered_sum_warp(l, cnt, grad_out, dst, D, lane, accumulate != 0, vec != 0);
             __syncthreads();
         } else {
             // pathological pile-up: selection in id order straight from global memory
@@ -383,9 +383,12 @@ cudaError_t launch_deterministic_grad_value_f32(const int64_t *shapes, const int
         det_count_fill_kernel<true><<<sample_blocks, 256, 0, stream>>>(shapes, lsi, loc, attn, count, cursor, start,
                                                                      records, d.S, d.M, d.L, d.P, d.Lq, samples,
                                                                       d.frame_q, d.frame_local, d.frame_slots);
+    // 128-bit loads / stores of the ordered sum need 16-byte aligned rows (a view with a storage offset, or a C
+    // caller's 4-byte aligned buffers, take the scalar branch instead of faulting)
+    const int vec = ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(grad_value)) & 15u) == 0 ? 1 : 0;
     const int64_t rblocks = (cells + kReduceWarps - 1) / kReduceWarps;
     det_reduce_kernel<<<(int)(rblocks < 148 * 32 ? rblocks : 148 * 32), 32 * kReduceWarps, 0, stream>>>(
-        grad_out, start, records, grad_value, long_cells, d.D, d.L * d.P, cells, accumulate ? 1 : 0);
+        grad_out, start, records, grad_value, long_cells, d.D, d.L * d.P, cells, accumulate ? 1 : 0, vec);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // over-long lists (none at Snipper's sizes unless many queries pile onto a coarse level)
@@ -393,7 +396,7 @@ cudaError_t launch_deterministic_grad_value_f32(const int64_t *shapes, const int
     e = cudaFuncSetAttribute(det_reduce_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem);
     if (e != cudaSuccess) return e;
     det_reduce_long_kernel<<<148, kLongThreads, long_smem, stream>>>(grad_out, start, records, grad_value, long_cells,
-                                                                    d.D, d.L * d.P, accumulate ? 1 : 0);
+                                                                    d.D, d.L * d.P, accumulate ? 1 : 0, vec);
     return cudaGetLastError();
 }
 

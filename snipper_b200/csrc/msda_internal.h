@@ -28,6 +28,10 @@ struct SnippetDims {
     // optional biases of the two Linear layers, added here instead of in a GEMM epilogue kernel
     const float *off_bias;    // (M, L, P, 2) or nullptr
     const float *logit_bias;  // (M, L, P) or nullptr
+    // encoder self-attention only (Lq == S, query q IS pixel q of the pyramid): when non-null the reference points are
+    // computed in-kernel from the query index instead of being read -- (N, L, 2) valid ratios (w, h) as built by
+    // DeformableTransformer.get_valid_ratio; reproduces get_reference_points (deformable_transformer.py:219-232) bit for bit
+    const float *valid_ratios;
     // presummed: `value` (and grad_value) hold one frame per SLOT (msda_frames.cu) instead of one per
     // source frame: (N, n_slots, S, M, D) with the strides above; each query frame gathers exactly one
     int presummed;

@@ -71,40 +71,57 @@ __device__ __forceinline__ unsigned lane_mask_bits(const uint8_t *__restrict__ m
     return bits;
 }
 
-template <typename C>
-__device__ __forceinline__ C masked_load(const char *__restrict__ vp, unsigned bits)
-{
-    C v = C::load(vp);
-#pragma unroll
-    for (int i = 0; i < C::N; ++i)
-        if (bits & (1u << i)) v.x[i] = 0.f;
-    return v;
-}
-
 struct MaskView {
     const uint8_t *p;      // mask element of (n, first gathered frame, cell 0, this lane's first channel)
     int64_t row, frame;    // bytes between consecutive cells / frames
     int col;
+    float inv_cell_bytes;  // 1 / (M * D * sizeof(VT))
 };
 
-// forward, all neighbour frames, every gathered chunk masked (value.masked_fill(mask, 0), ms_deform_attn.py:116-117)
+// cell index of a sample's (y0,x0) corner from its byte offset: off is a multiple of 16 below 2^28, hence exact in
+// fp32, and the quotient (< 2^24) survives the reciprocal's rounding -- no integer division in the gather loop
+__device__ __forceinline__ int cell_of(int off, float inv_cell_bytes)
+{
+    return __float2int_rn(__int2float_rn(off) * inv_cell_bytes);
+}
+
+// forward, all neighbour frames, every gathered chunk masked (value.masked_fill(mask, 0), ms_deform_attn.py:116-117).
+// The four mask reads and the four value reads of a frame are issued together (corners outside the level are
+// predicated off), then the FMAs: the few-queries launches this serves are latency-bound.
 template <typename VT>
 __device__ __forceinline__ void gather_fma_frames_masked(Chunk<VT> &acc, const SampleMeta mt, const float4 w,
                                                          const char *__restrict__ pf, int64_t frame_bytes, int nf,
-                                                         int csb, const MaskView &mv)
+                                                         int csb, int level_w, const MaskView &mv)
 {
     using C = Chunk<VT>;
     const unsigned cm = mt.wm >> 28;
     if (cm == 0u) return;
-    const int row = (int)(mt.wm & 0x0fffffffu);
-    const int64_t cell0 = mt.off / csb, wl = row / csb;   // exact: both are multiples of the cell stride
+    const ptrdiff_t row = (ptrdiff_t)(mt.wm & 0x0fffffffu);
     const char *a0 = pf + (ptrdiff_t)mt.off;
-    const uint8_t *m0 = mv.p + cell0 * mv.row;
+    const uint8_t *m0 = mv.p + (int64_t)cell_of(mt.off, mv.inv_cell_bytes) * mv.row;
+    const int64_t mrow = (int64_t)level_w * mv.row;
+    const ptrdiff_t vo[4] = {0, csb, row, row + csb};
+    const int64_t mo[4] = {0, mv.row, mrow, mrow + mv.row};
+    const float wk[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll 2
     for (int f = 0; f < nf; ++f, a0 += frame_bytes, m0 += mv.frame) {
-        if (cm & 1u) fma_chunk(acc, w.x, masked_load<C>(a0, lane_mask_bits<C::N>(m0, mv.col)));
-        if (cm & 2u) fma_chunk(acc, w.y, masked_load<C>(a0 + csb, lane_mask_bits<C::N>(m0 + mv.row, mv.col)));
-        if (cm & 4u) fma_chunk(acc, w.z, masked_load<C>(a0 + row, lane_mask_bits<C::N>(m0 + wl * mv.row, mv.col)));
-        if (cm & 8u) fma_chunk(acc, w.w, masked_load<C>(a0 + row + csb, lane_mask_bits<C::N>(m0 + (wl + 1) * mv.row, mv.col)));
+        unsigned bits[4];
+        C v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bits[k] = (1u << C::N) - 1u;      // an invalid corner reads as fully masked
+            v[k] = zero_chunk<C>();
+            if (cm & (1u << k)) {
+                bits[k] = lane_mask_bits<C::N>(m0 + mo[k], mv.col);
+                v[k] = C::load(a0 + vo[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int i = 0; i < C::N; ++i)
+                if (!(bits[k] & (1u << i))) acc.x[i] = fmaf(wk[k], v[k].x[i], acc.x[i]);
+        }
     }
 }
 
@@ -112,7 +129,8 @@ __device__ __forceinline__ void gather_fma_frames_masked(Chunk<VT> &acc, const S
 template <typename VT>
 __device__ __forceinline__ void gather_scatter_masked(const SampleMeta mt, const BwdWeights &b, const Chunk<VT> &g,
                                                       const RedView<VT> &gr, const char *__restrict__ p0, char *gp0,
-                                                      int csb, const uint8_t *__restrict__ m0, int64_t mrow, int mcol,
+                                                      int csb, int level_w, const uint8_t *__restrict__ m0,
+                                                      int64_t mrow, int mcol, float inv_cell_bytes,
                                                       float &pa, float &px, float &py)
 {
     using C = Chunk<VT>;
@@ -120,22 +138,34 @@ __device__ __forceinline__ void gather_scatter_masked(const SampleMeta mt, const
     constexpr int GS = 4 / (int)sizeof(typename C::elem);
     const unsigned cm = mt.wm >> 28;
     if (cm == 0u) return;
-    const int row = (int)(mt.wm & 0x0fffffffu);
-    const int64_t cell0 = mt.off / csb, wl = row / csb;
+    const ptrdiff_t row = (ptrdiff_t)(mt.wm & 0x0fffffffu);
+    const int64_t cell0 = cell_of(mt.off, inv_cell_bytes);
     const ptrdiff_t o[4] = {(ptrdiff_t)mt.off, (ptrdiff_t)mt.off + csb, (ptrdiff_t)mt.off + row, (ptrdiff_t)mt.off + row + csb};
-    const int64_t mc[4] = {cell0, cell0 + 1, cell0 + wl, cell0 + wl + 1};
+    const int64_t mc[4] = {cell0, cell0 + 1, cell0 + level_w, cell0 + level_w + 1};
     const float aw[4] = {b.a0, b.a1, b.a2, b.a3};
-    float dk[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned bits[4];
+    C v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (!(cm & (1u << k))) continue;
-        const unsigned bits = lane_mask_bits<4>(m0 + mc[k] * mrow, mcol);
-        dk[k] = dot_chunk(g, masked_load<C>(p0 + o[k], bits));
-        if (bits != 0xfu) {
+        bits[k] = 0xfu;
+        v[k] = zero_chunk<C>();
+        if (cm & (1u << k)) {
+            bits[k] = lane_mask_bits<4>(m0 + mc[k] * mrow, mcol);
+            v[k] = C::load(p0 + o[k]);
+        }
+    }
+    float dk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (bits[k] & (1u << i)) v[k].x[i] = 0.f;
+        dk[k] = dot_chunk(g, v[k]);
+        if (bits[k] != 0xfu) {
             RedView<VT> gm = gr;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (bits & (1u << i)) gm.x[i] = 0.f;
+                if (bits[k] & (1u << i)) gm.x[i] = 0.f;
             gm.red(gp0 + GS * o[k], aw[k]);
         }
     }
@@ -149,6 +179,24 @@ __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo
     // reference ms_deform_attn.py:137-140 (observed frames) and :189,201 (future frames)
     if (t1 < n_frame) { lo = max(t1 - 1, 0); hi = min(t1 + 1, n_frame - 1); }
     else { lo = 0; hi = T2 - 1; }
+}
+
+// Encoder reference points as a function of the query index (reference get_reference_points,
+// deformable_transformer.py:219-232): query q is pixel (y, x) of level lq; its reference point on level l is
+//     ( (x + 0.5) / (vr[n,lq,0] * W_lq) * vr[n,l,0],  (y + 0.5) / (vr[n,lq,1] * H_lq) * vr[n,l,1] )
+// -- same operations in the same order as the torch code (linspace(0.5, W - 0.5, W) is exactly x + 0.5), so the
+// result is bit-identical to the tensor the reference materialises and re-reads in every layer.
+__device__ __forceinline__ float2 analytic_reference_point(const LevelTable &lv, const float *__restrict__ vr, int L,
+                                                           int q, int l)
+{
+    int lq = 0;
+    while (lq + 1 < L && q >= lv.start[lq + 1]) ++lq;
+    const int Wq = max(lv.W[lq], 1);
+    const int r = q - lv.start[lq];
+    const int y = r / Wq, x = r - y * Wq;
+    const float rx = ((float)x + 0.5f) / (__ldg(vr + 2 * lq) * (float)lv.W[lq]);
+    const float ry = ((float)y + 0.5f) / (__ldg(vr + 2 * lq + 1) * (float)lv.H[lq]);
+    return make_float2(rx * __ldg(vr + 2 * l), ry * __ldg(vr + 2 * l + 1));
 }
 
 // Phase 1 of both kernels: one thread per sample.  Softmax over the L*P logits of each query (staged in
@@ -184,9 +232,13 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, LevelTabl
         if (q < d.Lq) {
             z = __ldg(logits + (qbase + q) * d.logit_row_stride + m * LP + lp);
             const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets + (qbase + q) * d.off_row_stride) + m * LP + lp);
-            const int l = fast_div(lp, a.magic_P);
-            const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
-            raw = make_float4(o.x, o.y, __ldg(rp), __ldg(rp + 1));
+            raw = make_float4(o.x, o.y, 0.f, 0.f);
+            if (d.valid_ratios == nullptr) {
+                const int l = fast_div(lp, a.magic_P);
+                const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+                raw.z = __ldg(rp);
+                raw.w = __ldg(rp + 1);
+            }
             if (d.logit_bias != nullptr) z += __ldg(d.logit_bias + m * LP + lp);
             if (d.off_bias != nullptr) {
                 const float2 b = __ldg(reinterpret_cast<const float2 *>(d.off_bias) + m * LP + lp);
@@ -211,7 +263,12 @@ __device__ __forceinline__ void snippet_phase1(float4 *rec, float *zs, LevelTabl
             for (int j = 0; j < LP; ++j) sum += expf(z[j] - mx);
             const float at = expf(z[lp] - mx) / sum * inv_k;
             const int l = fast_div(lp, a.magic_P);
-            const float4 raw = rec[i + spl];
+            float4 raw = rec[i + spl];
+            if (d.valid_ratios != nullptr) {
+                const float2 rp = analytic_reference_point(lv, d.valid_ratios + (size_t)n * d.L * 2, d.L, q0 + spl, l);
+                raw.z = rp.x;
+                raw.w = rp.y;
+            }
             const float u = raw.z + raw.x / (float)lv.W[l];
             const float v = raw.w + raw.y / (float)lv.H[l];
             const Sample<float> s = make_sample<float>(u, v, lv.H[l], lv.W[l], lv.start[l]);
@@ -265,11 +322,12 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + first * d.value_stride_t) +
                      (size_t)(m * LANES + chunk) * C::BYTES;
     const int64_t fstride = d.value_stride_t * (int64_t)sizeof(ET);  // bytes between frames
-    MaskView mv{nullptr, 0, 0, 0};
+    MaskView mv{nullptr, 0, 0, 0, 0.f};
     if (MODE == kDirectMasked) {
         mv.row = d.mask_row_stride;
         mv.frame = (int64_t)d.S * d.mask_row_stride;
         mv.col = d.mask_col_stride;
+        mv.inv_cell_bytes = 1.f / (float)a.cell_bytes;
         mv.p = d.mask + ((int64_t)n * d.T2 + lo) * mv.frame + (int64_t)((m * LANES + chunk) * C::N) * mv.col;
     }
     const float4 *rr = rec + pl * (LP + 1);
@@ -284,7 +342,7 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
                 gather_fma_frames<VT, CSB>(acc, record_meta(r, row), record_weights(r), pf, fstride, nf, a.cell_bytes);
             else
                 gather_fma_frames_masked<VT>(acc, record_meta(r, row), record_weights(r), pf, fstride, nf,
-                                             a.cell_bytes, mv);
+                                             a.cell_bytes, lv.W[l], mv);
         }
     }
     acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
@@ -355,7 +413,8 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
         float *mypart = part + (size_t)(pl * LP) * (Cfg::SUBS * 3) + sub * 3;
         for (int j = 0; j < LP; ++j) {
             const float4 f = ff[j];
-            const SampleMeta mt = record_meta(f, (unsigned)(lv.W[fast_div(j, a.magic_P)] * a.cell_bytes));
+            const int level_w = lv.W[fast_div(j, a.magic_P)];
+            const SampleMeta mt = record_meta(f, (unsigned)(level_w * a.cell_bytes));
             const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
             float pa = 0.f, px = 0.f, py = 0.f;
             const char *p0 = pf;
@@ -370,8 +429,8 @@ msda_snippet_bwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
             } else {
                 const uint8_t *mp = mpf;
                 for (int fr = 0; fr < nf; ++fr, p0 += fstride, gp0 += gfstride, mp += mframe)
-                    gather_scatter_masked<VT>(mt, bw, g, gr, p0, gp0, a.cell_bytes, mp, d.mask_row_stride,
-                                              d.mask_col_stride, pa, px, py);
+                    gather_scatter_masked<VT>(mt, bw, g, gr, p0, gp0, a.cell_bytes, level_w, mp, d.mask_row_stride,
+                                              d.mask_col_stride, 1.f / (float)a.cell_bytes, pa, px, py);
             }
             subgroup_sum3<Cfg::SUBG>(pa, px, py);
             // zs/es alias `part`: all phase-1 reads finished at the barrier that ends phase 1
@@ -573,10 +632,16 @@ snippet_loc_attn_kernel(const int64_t *__restrict__ shapes, const int64_t *__res
             const int l = j / d.P;
             float2 o = __ldg(orow + j);
             if (ob) { const float2 b = __ldg(ob + j); o.x += b.x; o.y += b.y; }
-            const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+            float2 r2;
+            if (d.valid_ratios != nullptr) {
+                r2 = analytic_reference_point(lv, d.valid_ratios + (size_t)n * d.L * 2, d.L, q, l);
+            } else {
+                const float *rp = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+                r2 = make_float2(__ldg(rp), __ldg(rp + 1));
+            }
             const int64_t si = i * LP + j;
-            loc[2 * si] = __ldg(rp) + o.x / (float)lv.W[l];
-            loc[2 * si + 1] = __ldg(rp + 1) + o.y / (float)lv.H[l];
+            loc[2 * si] = r2.x + o.x / (float)lv.W[l];
+            loc[2 * si + 1] = r2.y + o.y / (float)lv.H[l];
             attn[si] = expf(__ldg(zrow + j) + (zb ? __ldg(zb + j) : 0.f) - mx) / sum * inv_k;
         }
     }

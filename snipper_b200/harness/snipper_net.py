@@ -134,6 +134,7 @@ class Encoder(nn.Module):
     def __init__(self, layer, n):
         super().__init__()
         self.layers, self.num_layers = _clones(layer, n), n
+        self.analytic_reference_points = False   # snipper_b200.enable_fused_layer_tails: closed form, computed in-kernel
 
     @staticmethod
     def reference_points(sizes, valid_ratios, device):
@@ -149,7 +150,11 @@ class Encoder(nn.Module):
         return torch.cat(pts, 1)[:, :, None] * valid_ratios[:, None]  # (b, S, L, 2)
 
     def forward(self, src, sizes, shapes, lsi, valid_ratios, pos, mask, n_frame):
-        ref = self.reference_points(sizes, valid_ratios, src.device).unsqueeze(1).expand(-1, n_frame, -1, -1, -1)
+        if self.analytic_reference_points and not torch.is_grad_enabled():
+            from ..modules import EncoderGrid
+            ref = EncoderGrid(valid_ratios, sizes, n_frame)
+        else:
+            ref = self.reference_points(sizes, valid_ratios, src.device).unsqueeze(1).expand(-1, n_frame, -1, -1, -1)
         for layer in self.layers:
             src = layer(src, pos, ref, shapes, lsi, mask)
         return src

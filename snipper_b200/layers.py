@@ -10,7 +10,10 @@ loads) to a version that
     ONE kernel pass (``msda_layer_tail``), likewise for the FFN's second Linear;
   * lets the last tail of a layer also emit ``x + pos``, the next layer's query, so the separate
     ``with_pos_embed`` pass disappears;
-  * runs ``relu(linear1(x))`` as one cuBLASLt call with a bias+ReLU epilogue (stock library, no extra pass).
+  * runs ``relu(linear1(x))`` as one cuBLASLt call with a bias+ReLU epilogue (stock library, no extra pass);
+  * makes the ENCODER hand its layers an ``EncoderGrid`` instead of the materialised reference-point tensor
+    (get_reference_points, :219-232), so the fused kernels compute the reference points from the query index
+    (SURVEY.md section 8f rank 2).
 
 It applies in inference (autograd off or nothing requiring grad), fp32, dropout inactive; in every other
 situation the layer's ORIGINAL forward runs, so training behaviour is exactly the stock one.
@@ -24,7 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .modules import MSDeformAttn
+from .modules import EncoderGrid, MSDeformAttn
 
 _PLUS_POS = "_snipper_b200_plus_pos"   # attribute on a layer's output tensor: (pos tensor, output + pos)
 
@@ -98,6 +101,30 @@ def _decoder_forward(self, tgt, query_pos, reference_points, src, src_spatial_sh
     return out, vis
 
 
+def _reference_encoder_forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                               n_frame=1):
+    """reference DeformableTransformerEncoder.forward (deformable_transformer.py:234-241) without building the
+    (N,T,S,L,2) reference-point tensor: the layers receive its closed form (``EncoderGrid``)."""
+    if not (torch.is_tensor(spatial_shapes) and _eligible(self.layers[0], src)):
+        return self._stock_forward(src, spatial_shapes, level_start_index, valid_ratios, pos, padding_mask, n_frame)
+    grid = EncoderGrid(valid_ratios, _sizes_of(self, spatial_shapes), n_frame)
+    output = src
+    for layer in self.layers:
+        output = layer(output, pos, grid, spatial_shapes, level_start_index, padding_mask)
+    return output
+
+
+def _sizes_of(encoder, spatial_shapes):
+    """Python (H, W) pairs of a device shape tensor, read back ONCE per distinct tensor contents holder (the reference
+    itself iterates the device tensor in get_reference_points, i.e. synchronises every forward)."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape))
+    cache = encoder.__dict__.setdefault("_snipper_b200_sizes", {})
+    if key not in cache:
+        cache.clear()
+        cache[key] = [tuple(int(v) for v in row) for row in spatial_shapes.tolist()]
+    return cache[key]
+
+
 def _is_encoder_layer(m):
     return (isinstance(getattr(m, "self_attn", None), MSDeformAttn) and not hasattr(m, "cross_attn") and
             all(hasattr(m, a) for a in ("norm1", "norm2", "linear1", "linear2")))
@@ -125,14 +152,23 @@ def enable_fused_layer_tails(model):
             layer._emit_next_query = enc and i + 1 < len(layers) and _is_encoder_layer(layers[i + 1])
             layer.forward = types.MethodType(_encoder_forward if enc else _decoder_forward, layer)
             n += 1
+        # the encoder itself: in-kernel reference points
+        if len(layers) and all(_is_encoder_layer(l) for l in layers) and not hasattr(parent, "_stock_forward"):
+            if hasattr(parent, "analytic_reference_points"):          # the bench harness' encoder has a switch
+                parent.analytic_reference_points = True
+            elif hasattr(parent, "get_reference_points"):             # the reference's DeformableTransformerEncoder
+                parent._stock_forward = parent.forward
+                parent.forward = types.MethodType(_reference_encoder_forward, parent)
     return n
 
 
 def disable_fused_layer_tails(model):
     n = 0
     for m in model.modules():
+        if getattr(m, "analytic_reference_points", False) is True:
+            m.analytic_reference_points = False
         if hasattr(m, "_stock_forward") and "forward" in m.__dict__:
             del m.__dict__["forward"]
             del m.__dict__["_stock_forward"]
-            n += 1
+            n += _is_encoder_layer(m) or _is_decoder_layer(m)
     return n

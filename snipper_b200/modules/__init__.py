@@ -1,3 +1,3 @@
-from .ms_deform_attn import MSDeformAttn, neighbour_frames
+from .ms_deform_attn import EncoderGrid, MSDeformAttn, neighbour_frames
 
-__all__ = ["MSDeformAttn", "neighbour_frames"]
+__all__ = ["MSDeformAttn", "EncoderGrid", "neighbour_frames"]

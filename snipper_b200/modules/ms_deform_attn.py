@@ -38,6 +38,33 @@ def neighbour_frames(t1, n_frame, n_src_frames):
     return list(range(n_src_frames))
 
 
+class EncoderGrid:
+    """Stand-in for the ENCODER's ``reference_points`` tensor (reference get_reference_points,
+    models/deformable_transformer.py:219-232): the reference point of query q on level l is a closed-form function of
+    q and the per-level valid ratios, so the fused kernels compute it from the query index instead of reading a
+    (N,T,S,L,2) tensor that the reference materialises per forward and every layer re-reads.  Opt-in: pass an instance
+    as ``reference_points`` (snipper_b200.enable_fused_layer_tails does it for the encoder).  ``valid_ratios`` is
+    the (N,L,2) tensor of DeformableTransformer.get_valid_ratio; ``tensor()`` builds the reference's tensor (used by
+    the per-call fallback path and by tests)."""
+
+    def __init__(self, valid_ratios, spatial_sizes, n_frame):
+        self.valid_ratios = valid_ratios.float().contiguous()
+        self.spatial_sizes = [(int(h), int(w)) for h, w in spatial_sizes]
+        self.n_frame = n_frame
+
+    def tensor(self):
+        vr, dev = self.valid_ratios, self.valid_ratios.device
+        pts = []
+        for l, (H, W) in enumerate(self.spatial_sizes):
+            ys, xs = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=dev),
+                                    torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=dev), indexing="ij")
+            ys = ys.reshape(-1)[None] / (vr[:, None, l, 1] * H)
+            xs = xs.reshape(-1)[None] / (vr[:, None, l, 0] * W)
+            pts.append(torch.stack((xs, ys), -1))
+        ref = torch.cat(pts, 1)[:, :, None] * vr[:, None]
+        return ref.unsqueeze(1).expand(-1, self.n_frame, -1, -1, -1)
+
+
 class _LazyList(list):
     """A list whose elements are produced on first access (len, indexing, iteration)."""
 
@@ -212,12 +239,21 @@ class MSDeformAttn(nn.Module):
             proj = F.linear(query, weight)
             if proj.dtype != torch.float32:
                 proj = proj.float()
-            ref = reference_points if reference_points.dtype == torch.float32 else reference_points.float()
+            if isinstance(reference_points, EncoderGrid) and Lq == S:
+                ref, valid_ratios = None, reference_points.valid_ratios      # reference points computed in-kernel
+            else:
+                if isinstance(reference_points, EncoderGrid):
+                    reference_points = reference_points.tensor()
+                ref, valid_ratios = reference_points, None
+                if ref.dtype != torch.float32:
+                    ref = ref.float()
             out = ops.snippet_attention(value.view(N, T2, S, M, self.d_model // M), input_padding_mask,
                                         input_spatial_shapes, input_level_start_index, proj, off_bias, logit_bias,
-                                        ref, self.n_frame)
+                                        ref, self.n_frame, valid_ratios=valid_ratios)
             vis = None
             if self.attention_vis:
+                if ref is None:
+                    ref = reference_points.tensor()
                 vis = LazyVis(self, proj.detach(), off_bias.detach(), logit_bias.detach(), ref.detach(),
                               input_spatial_shapes, T2).lists()
         else:
@@ -227,6 +263,8 @@ class MSDeformAttn(nn.Module):
                     mask = mask.unsqueeze(-1)
                 value = value.masked_fill(mask, 0.0)
             value = value.view(N, T2, S, M, self.d_model // M)
+            if isinstance(reference_points, EncoderGrid):
+                reference_points = reference_points.tensor()
             out, vis = self._forward_per_call(query, reference_points, value, input_spatial_shapes,
                                               input_level_start_index)
         return out, vis

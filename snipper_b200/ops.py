@@ -316,7 +316,7 @@ def snippet_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Te
         status = capi.lib().msda_snippet_forward(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), out.data_ptr(),
-            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, 0, 0,
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, None, 0, 0,
             _DTYPES[value.dtype], 0, _stream(value.device))
     capi.check(status, "msda_snippet_forward")
     return out
@@ -346,7 +346,7 @@ def snippet_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: T
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             offsets.data_ptr(), logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(),
-            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, 0, 0,
+            N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 0, 0, None, None, None, None, 0, 0,
             _DTYPES[value.dtype], 0, None, 0, _stream(value.device))
     capi.check(status, "msda_snippet_backward")
     if value.dtype != torch.float32:
@@ -418,24 +418,32 @@ def num_slots(T1: int, n_frame: int) -> int:
 
 
 def _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref, n_frame,
-                  presummed=False, T2=None):
+                  presummed=False, T2=None, valid_ratios=None):
     for t, name in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
-                    (proj, "proj"), (ref, "reference_points")):
+                    (proj, "proj")) + (((ref, "reference_points"),) if ref is not None else ()):
         _require_cuda(t, name)
-    if value.dim() != 5 or proj.dim() != 4 or ref.dim() != 5:
+    if value.dim() != 5 or proj.dim() != 4 or (ref is not None and ref.dim() != 5):
         raise RuntimeError("expected value (N,T2,S,M,D), proj (N,T1,Lq,3*M*L*P), reference_points (N,T1,Lq,L,2)")
+    if (ref is None) == (valid_ratios is None):
+        raise RuntimeError("pass either reference_points or (encoder self-attention) valid_ratios")
     N, F, S, M, D = value.shape
     L = spatial_shapes.shape[0]
     Np, T1, Lq, W = proj.shape
     if Np != N or W % (3 * M * L) != 0:
         raise RuntimeError("proj must be (N,T1,Lq,3*M*L*P): [offsets (M,L,P,2) | logits (M,L,P)] per query")
     P = W // (3 * M * L)
-    if tuple(ref.shape) != (N, T1, Lq, L, 2) or tuple(spatial_shapes.shape) != (L, 2) or level_start_index.numel() != L:
-        raise RuntimeError("reference_points must be (N,T1,Lq,L,2), spatial_shapes (L,2), level_start_index (L,)")
+    if tuple(spatial_shapes.shape) != (L, 2) or level_start_index.numel() != L:
+        raise RuntimeError("spatial_shapes must be (L,2) and level_start_index (L,)")
+    if ref is not None and (tuple(ref.shape) != (N, T1, Lq, L, 2) or ref.dtype != torch.float32):
+        raise RuntimeError("reference_points must be float32 (N,T1,Lq,L,2)")
+    if valid_ratios is not None:
+        if (not valid_ratios.is_cuda or valid_ratios.dtype != torch.float32 or tuple(valid_ratios.shape) != (N, L, 2)
+                or not valid_ratios.is_contiguous() or Lq != S):
+            raise RuntimeError("valid_ratios must be contiguous float32 (N,L,2) and the queries the S pixels of the pyramid")
     if not snippet_supported(M, D, L, P, value.dtype, S, N * T1):
         raise RuntimeError("fused snippet attention needs float32 / bfloat16 value, D % 16 == 0, D <= 128, L*P <= 32")
-    if proj.dtype != torch.float32 or ref.dtype != torch.float32:
-        raise RuntimeError("proj and reference_points must be float32")
+    if proj.dtype != torch.float32:
+        raise RuntimeError("proj must be float32")
     for b, n in ((offsets_bias, 2 * M * L * P), (logits_bias, M * L * P)):
         if b is not None and (not b.is_cuda or b.dtype != torch.float32 or b.numel() != n or not b.is_contiguous()):
             raise RuntimeError("biases must be contiguous float32 CUDA tensors of 2*M*L*P / M*L*P elements")
@@ -468,20 +476,31 @@ def _frame_sum(value, mask, mrs, mcs, T1, n_frame):
     return vsum
 
 
+def _ref_args(reference_points, valid_ratios):
+    """-> (tensor to keep alive, ref pointer, batch stride, frame stride, valid-ratio pointer)"""
+    if reference_points is None:
+        return None, None, 0, 0, valid_ratios.data_ptr()
+    ref, rsn, rst = _ref_strides(reference_points)
+    return ref, ref.data_ptr(), rsn, rst, None
+
+
 @torch.library.custom_op("snipper_b200::snippet_attn", mutates_args=())
 def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor, level_start_index: Tensor,
                  proj: Tensor, offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
-                 reference_points: Tensor, n_frame: int, presum: bool) -> Tuple[Tensor, Tensor]:
+                 reference_points: Optional[Tensor], valid_ratios: Optional[Tensor], n_frame: int,
+                 presum: bool) -> Tuple[Tensor, Tensor]:
     """The whole per-frame loop of the reference module (ms_deform_attn.py:116-117,126-225) for one layer.
 
     value (N,T2,S,M,D) is the raw ``value_proj`` output; ``value_mask`` the padding mask over it (any layout
-    ``mask_layout`` accepts) or None; proj (N,T1,Lq,3*M*L*P) = [offsets | logits] without biases.
+    ``mask_layout`` accepts) or None; proj (N,T1,Lq,3*M*L*P) = [offsets | logits] without biases;
+    ``reference_points`` (N,T1,Lq,L,2), or None with ``valid_ratios`` (N,L,2) for the encoder's self-attention,
+    whose reference points the kernel then derives from the query index (deformable_transformer.py:219-232).
     Returns (out (N,T1,Lq,M*D), carry): carry is the presummed value (N,slots,S,M,D) when ``presum`` -- the
     only form of value the backward needs -- and an empty tensor otherwise."""
     N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
-                                                 logits_bias, reference_points, n_frame)
+                                                 logits_bias, reference_points, n_frame, valid_ratios=valid_ratios)
     mask, mrs, mcs = mask_layout(value_mask, N, T2, S, M * D)
-    ref, rsn, rst = _ref_strides(reference_points)
+    ref, ref_ptr, rsn, rst, vr_ptr = _ref_args(reference_points, valid_ratios)
     mlp = M * L * P
     out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
     dims = (N, T2, T1, S, M, D, L, Lq, P)
@@ -495,9 +514,9 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
     with torch.cuda.device(value.device), _Launch(tag, dims, value.device):
         status = capi.lib().msda_snippet_forward(
             src.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), out.data_ptr(),
+            proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref_ptr, out.data_ptr(),
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
-            _ptr(offsets_bias), _ptr(logits_bias), _ptr(kmask), mrs, mcs,
+            _ptr(offsets_bias), _ptr(logits_bias), vr_ptr, _ptr(kmask), mrs, mcs,
             _DTYPES[value.dtype], flags, _stream(value.device))
     capi.check(status, "msda_snippet_forward")
     return out, carry
@@ -505,7 +524,7 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
 
 @snippet_attn.register_fake
 def _(value, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points,
-      n_frame, presum):
+      valid_ratios, n_frame, presum):
     N, T2, S, M, D = value.shape
     out = value.new_empty((N, proj.shape[1], proj.shape[2], M * D))
     if presum:
@@ -516,20 +535,21 @@ def _(value, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, 
 @torch.library.custom_op("snipper_b200::snippet_attn_backward", mutates_args=())
 def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor,
                           level_start_index: Tensor, proj: Tensor, offsets_bias: Optional[Tensor],
-                          logits_bias: Optional[Tensor], reference_points: Tensor, grad_output: Tensor,
+                          logits_bias: Optional[Tensor], reference_points: Optional[Tensor],
+                          valid_ratios: Optional[Tensor], grad_output: Tensor,
                           n_frame: int, presum: bool, n_src_frames: int, deterministic: bool) -> Tuple[Tensor, Tensor]:
     """Returns (grad_value (N,T2,S,M,D) in value's dtype, grad_proj with proj's layout [grad_offsets | grad_logits]).
     ``value_or_vsum`` is what the forward carried: the presummed value when ``presum``, else value itself."""
     N, T2, T1, S, M, D, L, Lq, P = _check_packed(value_or_vsum, spatial_shapes, level_start_index, proj,
                                                  offsets_bias, logits_bias, reference_points, n_frame,
-                                                 presummed=presum, T2=n_src_frames)
+                                                 presummed=presum, T2=n_src_frames, valid_ratios=valid_ratios)
     _require_cuda(grad_output, "grad_output")
     _require_contiguous(grad_output, "grad_output")
     if grad_output.dtype != value_or_vsum.dtype or grad_output.numel() != N * T1 * Lq * M * D:
         raise RuntimeError("grad_output must be (N,T1,Lq,M*D) in value's dtype")
     dev, dt = value_or_vsum.device, value_or_vsum.dtype
     mask, mrs, mcs = mask_layout(value_mask, N, T2, S, M * D)
-    ref, rsn, rst = _ref_strides(reference_points)
+    ref, ref_ptr, rsn, rst, vr_ptr = _ref_args(reference_points, valid_ratios)
     mlp = M * L * P
     grad_proj = torch.empty_like(proj)
     dims = (N, T2, T1, S, M, D, L, Lq, P)
@@ -550,10 +570,11 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
         with torch.cuda.device(dev), _Launch(tag, dims, dev, n_kernels):
             status = L_.msda_snippet_backward(
                 value_or_vsum.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
+                proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref_ptr, grad_output.data_ptr(),
                 gsum.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
                 N, T2, T1, int(n_frame), S, M, D, L, Lq, P, 0, 0, rsn, rst, 3 * mlp, 3 * mlp,
-                _ptr(offsets_bias), _ptr(logits_bias), None, 0, 0, _DTYPES[dt], flags, ws_ptr, ws_bytes, _stream(dev))
+                _ptr(offsets_bias), _ptr(logits_bias), vr_ptr, None, 0, 0, _DTYPES[dt], flags, ws_ptr, ws_bytes,
+                _stream(dev))
         capi.check(status, "msda_snippet_backward")
         grad_value = torch.empty((N, T2, S, M, D), dtype=dt, device=dev)
         with torch.cuda.device(dev), _Launch("frame_unsum", (N, T2, T1, S, M * D), dev):
@@ -566,10 +587,10 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
     with torch.cuda.device(dev), _Launch("snippet_backward", dims, dev, 2):
         status = L_.msda_snippet_backward(
             value_or_vsum.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref.data_ptr(), grad_output.data_ptr(),
+            proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref_ptr, grad_output.data_ptr(),
             grad_value.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
             N, T2, T1, int(n_frame), S, M, D, L, Lq, P, sn, st, rsn, rst, 3 * mlp, 3 * mlp,
-            _ptr(offsets_bias), _ptr(logits_bias), _ptr(mask), mrs, mcs, _DTYPES[dt], 0, None, 0, _stream(dev))
+            _ptr(offsets_bias), _ptr(logits_bias), vr_ptr, _ptr(mask), mrs, mcs, _DTYPES[dt], 0, None, 0, _stream(dev))
     capi.check(status, "msda_snippet_backward")
     if dt != torch.float32:
         grad_value = grad_value.to(dt)
@@ -578,33 +599,33 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
 
 @snippet_attn_backward.register_fake
 def _(value_or_vsum, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias,
-      reference_points, grad_output, n_frame, presum, n_src_frames, deterministic):
+      reference_points, valid_ratios, grad_output, n_frame, presum, n_src_frames, deterministic):
     N, _, S, M, D = value_or_vsum.shape
     return value_or_vsum.new_empty((N, n_src_frames, S, M, D)), torch.empty_like(proj)
 
 
 def _attn_setup_context(ctx, inputs, output):
-    value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, reference_points, n_frame, presum = inputs
+    (value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, reference_points, valid_ratios, n_frame,
+     presum) = inputs
     out, carry = output
     ctx.n_frame, ctx.presum, ctx.T2 = n_frame, bool(presum), value.shape[1]
-    ctx.flags = (ob is not None, lb is not None, value_mask is not None)
+    ctx.flags = (reference_points is not None, valid_ratios is not None, ob is not None, lb is not None,
+                 value_mask is not None)
     # the presummed value replaces value itself: the backward reads nothing else of it
     ctx.save_for_backward(*[t for t in (carry if presum else value, spatial_shapes, level_start_index, proj,
-                                        reference_points, ob, lb, value_mask) if t is not None])
+                                        reference_points, valid_ratios, ob, lb, value_mask) if t is not None])
     ctx.set_materialize_grads(False)
 
 
 def _attn_backward_formula(ctx, grad_output, grad_carry):
     saved = list(ctx.saved_tensors)
-    value, spatial_shapes, level_start_index, proj, ref = saved[:5]
-    rest = saved[5:]
-    ob = rest.pop(0) if ctx.flags[0] else None
-    lb = rest.pop(0) if ctx.flags[1] else None
-    value_mask = rest.pop(0) if ctx.flags[2] else None
+    value, spatial_shapes, level_start_index, proj = saved[:4]
+    rest = saved[4:]
+    ref, vr, ob, lb, value_mask = [rest.pop(0) if f else None for f in ctx.flags]
     if grad_output is None:
-        return (None,) * 10
+        return (None,) * 11
     gv, gproj = torch.ops.snipper_b200.snippet_attn_backward(
-        value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, ref, grad_output.contiguous(),
+        value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, ref, vr, grad_output.contiguous(),
         ctx.n_frame, ctx.presum, ctx.T2, _deterministic)
     N, _, S, M, D = value.shape
     L = spatial_shapes.shape[0]
@@ -615,11 +636,11 @@ def _attn_backward_formula(ctx, grad_output, grad_carry):
         col = gproj.sum(dim=(0, 1, 2))                       # bias gradients = column sums of the projection gradient
         gob = col[:2 * mlp] if ctx.needs_input_grad[5] else None
         glb = col[2 * mlp:] if ctx.needs_input_grad[6] else None
-    if ctx.needs_input_grad[7]:
+    if ref is not None and ctx.needs_input_grad[7]:
         goff = gproj[..., :2 * mlp].view(proj.shape[0], proj.shape[1], proj.shape[2], M, L, P, 2)
         wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
         gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
-    return gv, None, None, None, gproj, gob, glb, gref, None, None
+    return gv, None, None, None, gproj, gob, glb, gref, None, None, None
 
 
 snippet_attn.register_autograd(_attn_backward_formula, setup_context=_attn_setup_context)
@@ -627,15 +648,18 @@ snippet_attn.register_autograd(_attn_backward_formula, setup_context=_attn_setup
 
 def snippet_attention(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor, level_start_index: Tensor,
                       proj: Tensor, offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
-                      reference_points: Tensor, n_frame: int, presum: Optional[bool] = None) -> Tensor:
-    """Fused layer attention; picks the neighbour-frame strategy (``presum=None``) from the shapes."""
+                      reference_points: Optional[Tensor], n_frame: int, presum: Optional[bool] = None,
+                      valid_ratios: Optional[Tensor] = None) -> Tensor:
+    """Fused layer attention; picks the neighbour-frame strategy (``presum=None``) from the shapes.
+    ``reference_points=None, valid_ratios=(N,L,2)``: encoder self-attention with in-kernel reference points."""
     N, T2, S, M, D = value.shape
     _, T1, Lq, W = proj.shape
     L = spatial_shapes.shape[0]
     if presum is None:
         presum = prefers_presum(T2, T1, n_frame, S, L, Lq, W // (3 * M * L)) or (_deterministic and torch.is_grad_enabled())
     out, _ = torch.ops.snipper_b200.snippet_attn(value, value_mask, spatial_shapes, level_start_index, proj,
-                                                 offsets_bias, logits_bias, reference_points, n_frame, bool(presum))
+                                                 offsets_bias, logits_bias, reference_points, valid_ratios, n_frame,
+                                                 bool(presum))
     return out
 
 

@@ -258,3 +258,40 @@ def test_module_deterministic_mode_stays_on_the_fused_path():
         assert torch.equal(x, y)                       # bit-identical run to run
     for x, y in zip(g1, want):
         assert rel_err(x, y) < 1e-4                    # and the same gradients as the atomic path
+
+
+def test_encoder_reference_points_in_kernel_are_bit_identical():
+    """the encoder's reference points as a function of the query index (valid ratios in, no
+    (N,T,S,L,2) tensor) reproduce get_reference_points (deformable_transformer.py:219-232) bit for bit -- forward,
+    every gradient, atomic-free deterministic mode included."""
+    import snipper_b200
+    from snipper_b200 import ops
+    from snipper_b200.modules import EncoderGrid
+    S = sum(h * w for h, w in LEVELS)
+    c = _case(2, 4, 4, S, seed=41, encoder=True)
+    g = torch.Generator().manual_seed(9)
+    vr = (torch.rand(2, 3, 2, generator=g) * 0.4 + 0.6).to(DEV)           # padded frames: valid ratios < 1
+    grid = EncoderGrid(vr, LEVELS, 4)
+    ref = grid.tensor().contiguous()
+    value = c["value"].to(DEV)
+    proj, ob, lb = c["proj"].to(DEV), c["off_bias"].to(DEV), c["logit_bias"].to(DEV)
+    shapes, lsi, pix, go = c["shapes"].to(DEV), c["lsi"].to(DEV), c["pix"].to(DEV), c["grad_out"].to(DEV)
+
+    def run(reference_points, valid_ratios, deterministic):
+        snipper_b200.set_deterministic(deterministic)
+        try:
+            v, p = value.clone().requires_grad_(True), proj.clone().requires_grad_(True)
+            out = ops.snippet_attention(v, pix, shapes, lsi, p, ob, lb, reference_points, 4, valid_ratios=valid_ratios)
+            out.backward(go)
+            return out.detach(), v.grad, p.grad
+        finally:
+            snipper_b200.set_deterministic(False)
+
+    a = run(ref, None, True)
+    b = run(None, vr, True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    a = run(ref, None, False)
+    b = run(None, vr, False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])           # grad_value differs only by atomic ordering
+    assert rel_err(b[1], a[1]) < 1e-5

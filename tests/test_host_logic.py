@@ -50,11 +50,11 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert L.msda_masked_zero(256, 256, 16, F64, 0) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
     assert L.msda_masked_zero(256, 257, 16, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
     # msda_snippet_forward(value, shapes, lsi, offsets, logits, ref, out, N,T2,T1,n_frame,S,M,D,L,Lq,P, strides x6,
-    #                      biases x2, mask, mask row / col stride, dtype, flags, stream)
+    #                      biases x2, encoder valid ratios, mask, mask row / col stride, dtype, flags, stream)
     def fwd(N=1, T2=4, T1=4, n_frame=4, S=100, M=8, D=48, Lv=3, Lq=10, P=4, ors=0, lrs=0, dtype=F32, ptr=256,
-            mask=None, mrs=0, mcs=0, flags=0):
+            mask=None, mrs=0, mcs=0, flags=0, vr=None):
         return L.msda_snippet_forward(ptr, ptr, ptr, ptr, ptr, ptr, ptr, N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                      0, 0, 0, 0, ors, lrs, None, None, mask, mrs, mcs, dtype, flags, 0)
+                                      0, 0, 0, 0, ors, lrs, None, None, vr, mask, mrs, mcs, dtype, flags, 0)
     assert fwd(N=0) == capi.MSDA_OK and fwd(Lq=0) == capi.MSDA_OK          # empty problems: nothing is launched
     assert fwd(n_frame=5) == capi.MSDA_ERR_INVALID_ARGUMENT                 # n_frame > T2
     assert fwd(D=40) == capi.MSDA_ERR_INVALID_ARGUMENT                      # D % 16 != 0
@@ -71,10 +71,12 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert fwd(N=0, mask=256, mrs=384, mcs=1, flags=capi.MSDA_FLAG_PRESUMMED) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert fwd(N=0, flags=capi.MSDA_FLAG_PRESUMMED) == capi.MSDA_OK
     assert fwd(N=0, flags=64) == capi.MSDA_ERR_INVALID_ARGUMENT
+    # in-kernel encoder reference points: the queries must be the pixels of the pyramid (Lq == S)
+    assert fwd(N=0, vr=256, Lq=100) == capi.MSDA_OK and fwd(N=0, vr=256, Lq=10) == capi.MSDA_ERR_INVALID_ARGUMENT
     # deterministic mode of the fused layer: pre-summed float32 only, needs its workspace
     def bwd(flags, dtype=F32, ws=None, ws_bytes=0):
         return L.msda_snippet_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 4, 4, 4, 100, 8, 48, 3, 10, 4,
-                                       0, 0, 0, 0, 0, 0, None, None, None, 0, 0, dtype, flags, ws, ws_bytes, 0)
+                                       0, 0, 0, 0, 0, 0, None, None, None, None, 0, 0, dtype, flags, ws, ws_bytes, 0)
     DET, PRE = capi.MSDA_FLAG_DETERMINISTIC, capi.MSDA_FLAG_PRESUMMED
     assert bwd(DET) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert bwd(DET | PRE, dtype=BF16) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
@@ -98,6 +100,13 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert fsum(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert L.msda_frame_unsum(0, None, 0, 0, 4, 4, 4, 100, 384, 0, 0, F32, 0) == capi.MSDA_OK
     assert L.msda_frame_unsum(0, None, 0, 1, 4, 4, 4, 100, 384, 0, 0, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
+    # layer tail: float32 rows of 128*k <= 1024 channels; pos and its output come together
+    tail = lambda rows=4, cols=384, dtype=F32, pos=None, out2=None, ptr=256: L.msda_layer_tail(
+        ptr, ptr, ptr, ptr, ptr, pos, ptr, out2, rows, cols, 1e-5, dtype, 0)
+    assert tail(rows=0) == capi.MSDA_OK
+    assert tail(cols=100) == capi.MSDA_ERR_INVALID_ARGUMENT and tail(cols=2048) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert tail(dtype=BF16) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert tail(pos=256) == capi.MSDA_ERR_INVALID_ARGUMENT and tail(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT
     # deterministic mode: 32-bit corner ids -> a clear error instead of a wrong answer
     assert L.msda_backward(256, 256, 256, 256, 256, 256, 256, 256, 256, 64, 9875, 8, 48, 12, 9875 * 4, 8, 0, 64, F32,
                            capi.MSDA_FLAG_DETERMINISTIC, 256, 1 << 40, 0) == capi.MSDA_ERR_TOO_LARGE
@@ -135,11 +144,12 @@ def test_fake_kernels_give_shapes_without_a_device():
     ref = torch.empty(2, 6, 7, 3, 2, device="meta")
     assert torch.ops.snipper_b200.snippet_forward(v5, sh, lsi, off, lg, ref, 4).shape == (2, 6, 7, 384)
     proj = torch.empty(2, 6, 7, 3 * 8 * 3 * 4, device="meta")
-    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, 4, True)
+    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, None, 4, True)
     assert out.shape == (2, 6, 7, 384) and carry.shape == (2, 5, 50, 8, 48)      # 4 frame slots + the all-frames slot
-    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, 4, False)
+    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, None, 4, False)
     assert out.shape == (2, 6, 7, 384) and carry.numel() == 0
-    gv, gp = torch.ops.snipper_b200.snippet_attn_backward(v5, None, sh, lsi, proj, None, None, ref, out, 4, False, 4, False)
+    gv, gp = torch.ops.snipper_b200.snippet_attn_backward(v5, None, sh, lsi, proj, None, None, ref, None, out, 4, False, 4,
+                                                          False)
     assert gv.shape == v5.shape and gp.shape == proj.shape
 
 

@@ -66,6 +66,7 @@ def test_fused_layer_tails_reproduce_the_stock_layers(future):
     with torch.no_grad():
         want, (_, w_refs, w_att) = net(x)
         assert snipper_b200.enable_fused_layer_tails(net) == 5
+        assert net.transformer.encoder.analytic_reference_points        # reference points computed in-kernel from now on
         ops.STATS.reset()
         ops.STATS.timing = True
         got, (_, g_refs, g_att) = net(x)

@@ -24,7 +24,9 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), re
 DEV = "cuda:0"
 KW = dict(hidden_dim=384, nheads=8, num_feature_levels=3, enc_n_points=4, dec_n_points=4, num_frames=4,
           num_future_frames=2, enc_layers=2, dec_layers=2, num_queries=9, dim_feedforward=256, dropout=0.0)
-FWD_TOL, BWD_TOL = 1e-4, 2e-3   # whole network (ResNet-50 + 4 attention layers) in fp32 on one device, two op orders
+# whole network (ResNet-50 + 4 attention layers + heads) in fp32, two formulations of every attention call; the
+# gradient tolerances are those of tests/test_model_gpu.py (backbone convolutions: cuDNN algorithm choice is looser)
+FWD_TOL, BWD_TOL, BWD_TOL_BACKBONE = 1e-4, 5e-3, 3e-2
 
 
 @pytest.fixture(autouse=True)
@@ -89,8 +91,10 @@ def _compare(got, want):
     for i, (a, b) in enumerate(zip(got[0], want[0])):
         assert rel_err(a, b) < FWD_TOL, ("output", i, rel_err(a, b))
     assert set(got[1]) == set(want[1])
-    worst = max((rel_err(got[1][n], want[1][n]), n) for n in want[1] if float(want[1][n].abs().max()) > 0)
-    assert worst[0] < BWD_TOL, worst
+    errs = sorted(((rel_err(got[1][n], want[1][n]), n) for n in want[1] if float(want[1][n].abs().max()) > 1e-8), reverse=True)
+    assert len(errs) > 50
+    for e, n in errs:
+        assert e < (BWD_TOL_BACKBONE if n.startswith("backbone.") else BWD_TOL), errs[:5]
 
 
 def test_extension_shim_runs_the_unmodified_reference():
@@ -108,8 +112,9 @@ def test_extension_shim_runs_the_unmodified_reference():
         assert _set_deform_path(model, use_pytorch=False) == KW["enc_layers"] + KW["dec_layers"]
         ops.STATS.reset()
         got = _run(model, x, w)
-        # 10 (t1,t2) pairs per encoder layer, 10 + 2*4 per decoder layer (T = 4 + 2), forward and backward
-        assert ops.STATS.launches == 2 * (KW["enc_layers"] * 10 + KW["dec_layers"] * 18)
+        # 10 (t1,t2) pairs per encoder layer, 10 + 2*4 per decoder layer (T = 4 + 2): one forward launch and one
+        # grad_value memset + one backward launch per pair
+        assert ops.STATS.launches == 3 * (KW["enc_layers"] * 10 + KW["dec_layers"] * 18)
     finally:
         if before is not None:
             ref_func.MSDA = before
@@ -150,3 +155,39 @@ def test_fused_module_builds_into_the_unmodified_reference():
             assert a.shape == b.shape and rel_err(a, b) < FWD_TOL
         for a, b in zip(w_o, w_r):
             assert a.shape == b.shape and rel_err(a, b) < FWD_TOL
+
+
+def test_fused_layer_tails_on_the_reference_layers():
+    """The opt-in layer tails + in-kernel encoder reference points applied to the REFERENCE's own layer / encoder
+    classes (built with the fused module): inference outputs of the whole network stay at the forward tolerance."""
+    import snipper_b200
+    from snipper_b200 import ops
+    import models.ops.modules as ref_modules
+    model = _reference_model()
+    x = torch.rand(1, 3 * KW["num_frames"], 192, 256, device=DEV)
+    ref_cls = ref_modules.MSDeformAttn
+    try:
+        snipper_b200.install_module()
+        torch.manual_seed(3)
+        ours, _ = ref_loader.build_reference_model(use_pytorch_deform=0, **KW)
+    finally:
+        for name in ("models.ops.modules", "models.ops.modules.ms_deform_attn", "models.deformable_transformer"):
+            sys.modules[name].MSDeformAttn = ref_cls
+    ours.load_state_dict(model.state_dict(), strict=True)
+    ours = ours.to(DEV).eval()
+    assert snipper_b200.enable_fused_layer_tails(ours) == KW["enc_layers"] + KW["dec_layers"]
+    assert "forward" in ours.transformer.encoder.__dict__                 # the reference's encoder hands out an EncoderGrid
+    with torch.no_grad():
+        want, _ = model(x)
+        ops.STATS.reset()
+        ops.STATS.timing = True
+        got, _ = ours(x)
+        ops.STATS.timing = False
+    assert len([e for e in ops.STATS.events if e[0] == "layer_tail"]) == 2 * KW["enc_layers"] + 3 * KW["dec_layers"]
+    for k in ("pred_logits", "pred_kpts2d", "pred_depth"):
+        assert rel_err(got[k], want[k]) < FWD_TOL, k
+    for a, b in zip(got["heatmaps"], want["heatmaps"]):
+        assert rel_err(a, b) < FWD_TOL
+    assert sorted(ours.state_dict().keys()) == sorted(model.state_dict().keys())
+    assert snipper_b200.disable_fused_layer_tails(ours) == KW["enc_layers"] + KW["dec_layers"]
+    assert "forward" not in ours.transformer.encoder.__dict__

@@ -194,14 +194,14 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
     def fwd():
         r = L.msda_snippet_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                    logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
-                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, 0, st)
+                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, 0, st)
         assert r == 0, r
 
     def bwd():
         r = L.msda_snippet_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, 0, None, 0, st)
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, 0, None, 0, st)
         assert r == 0, r
 
     # neighbour-frame pre-summation: streaming pass + one gather per query frame (and the mirror in the backward)
@@ -221,14 +221,14 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
     def fwd_pre():
         r = L.msda_snippet_forward(vsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                    logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
-                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, PRE, st)
+                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, PRE, st)
         assert r == 0, r
 
     def bwd_pre():
         r = L.msda_snippet_backward(vsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gsum.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, PRE, None, 0, st)
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, PRE, None, 0, st)
         assert r == 0, r
 
     def funsum():
@@ -245,7 +245,7 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
         r = L.msda_snippet_backward(vsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
                                     logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gsum.data_ptr(),
                                     goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
-                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, 0, 0, dt, DET, ws_ptr, ws_bytes, st)
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, DET, ws_ptr, ws_bytes, st)
         assert r == 0, r
 
     def layer_fwd_pre():
