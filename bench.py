@@ -195,6 +195,9 @@ def kernel_table(per_kernel, steps, bf16):
         elif tag == "frame_unsum":
             N, T2, T1, S, C = dims
             nbytes = N * S * C * (4 * (min(T1, T2) + (1 if T1 > T2 else 0)) + e * T2)
+        elif tag == "layer_tail":          # reads y + residual (+ pos), writes out (+ out + pos); fp32
+            rows, C, with_pos = dims
+            nbytes = 4 * rows * C * (3 + 2 * with_pos)
         rows.append({"kernel": tag, "dims": "x".join(map(str, dims)), "launches_per_step": len(ms) / steps,
                      "avg_us": round(avg * 1e3, 2), "ms_per_step": round(sum(ms) / steps, 4),
                      "algorithmic_MB": None if nbytes is None else round(nbytes / 1e6, 2),
@@ -385,6 +388,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-fused-tails", action="store_true", help="keep the stock layer tails (A/B of SURVEY 8f rank 3)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"],
                     help="NOT the headline: 'tf32' lets cuBLAS use TF32 tensor cores for the stock Linear layers, "
                          "'bf16' runs the network under torch.autocast(bfloat16) (bf16 GEMMs, bf16 MSDA gathers). "
@@ -419,6 +423,8 @@ def main():
     autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if bf16 else contextlib.nullcontext
     torch.manual_seed(42)  # reference main.py:48
     model = build_snipper(snipper_b200.MSDeformAttn).to(dev).eval()
+    # the package's opt-in layer tails (bias + residual + LayerNorm (+ pos) in one pass) and in-kernel encoder reference points
+    fused_tails = 0 if args.no_fused_tails else snipper_b200.enable_fused_layer_tails(model)
     # snippet sharding: every rank takes its own contiguous slice of the job's snippets (no data-path collective)
     lo, hi = sharding.shard_range(N_INPUTS * world, rank, world)
     host = [x.pin_memory() for x in synthetic_snippets(hi - lo, seed=1000 + rank)]
@@ -545,6 +551,7 @@ def main():
                    "weights": "random init (seed 42): sampling offsets are the fixed per-head grid, best-case gather locality",
                    "precision_note": "fp32 = torch defaults: fp32 SIMT GEMMs for the Linear layers, cuDNN convolutions may use TF32 "
                                      "(torch.backends.cudnn.allow_tf32 default); the CPU arm is strict fp32",
+                   "fused_layer_tails": "%d layers (snipper_b200.enable_fused_layer_tails)" % fused_tails,
                    "msda_ms_per_step_eager_events": msda_ms_per_step},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps},

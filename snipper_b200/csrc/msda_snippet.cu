@@ -85,9 +85,21 @@ __device__ __forceinline__ int cell_of(int off, float inv_cell_bytes)
     return __float2int_rn(__int2float_rn(off) * inv_cell_bytes);
 }
 
+// != 0 <=> some channel of the lane's chunk is masked (the cheap test; lane_mask_bits says which)
+template <int N>
+__device__ __forceinline__ unsigned lane_mask_any(const uint8_t *__restrict__ mp, int col_stride)
+{
+    if (col_stride == 0) return __ldg(mp);
+    unsigned any = 0u;
+#pragma unroll
+    for (int w = 0; w < N / 4; ++w) any |= __ldg(reinterpret_cast<const unsigned *>(mp) + w);
+    return any;
+}
+
 // forward, all neighbour frames, every gathered chunk masked (value.masked_fill(mask, 0), ms_deform_attn.py:116-117).
 // The four mask reads and the four value reads of a frame are issued together (corners outside the level are
-// predicated off), then the FMAs: the few-queries launches this serves are latency-bound.
+// predicated off); padding is rare, so the common case -- no masked channel under any corner -- runs the plain
+// 16 FMAs and only samples next to padding take the per-channel path.
 template <typename VT>
 __device__ __forceinline__ void gather_fma_frames_masked(Chunk<VT> &acc, const SampleMeta mt, const float4 w,
                                                          const char *__restrict__ pf, int64_t frame_bytes, int nf,
@@ -105,22 +117,28 @@ __device__ __forceinline__ void gather_fma_frames_masked(Chunk<VT> &acc, const S
     const float wk[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll 2
     for (int f = 0; f < nf; ++f, a0 += frame_bytes, m0 += mv.frame) {
-        unsigned bits[4];
+        unsigned any = 0u;
         C v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            bits[k] = (1u << C::N) - 1u;      // an invalid corner reads as fully masked
-            v[k] = zero_chunk<C>();
+            v[k] = zero_chunk<C>();             // a corner outside the level contributes nothing
             if (cm & (1u << k)) {
-                bits[k] = lane_mask_bits<C::N>(m0 + mo[k], mv.col);
+                any |= lane_mask_any<C::N>(m0 + mo[k], mv.col);
                 v[k] = C::load(a0 + vo[k]);
             }
         }
+        if (any == 0u) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k) fma_chunk(acc, wk[k], v[k]);
+        } else {
 #pragma unroll
-            for (int i = 0; i < C::N; ++i)
-                if (!(bits[k] & (1u << i))) acc.x[i] = fmaf(wk[k], v[k].x[i], acc.x[i]);
+            for (int k = 0; k < 4; ++k) {
+                if (!(cm & (1u << k))) continue;
+                const unsigned bits = lane_mask_bits<C::N>(m0 + mo[k], mv.col);
+#pragma unroll
+                for (int i = 0; i < C::N; ++i)
+                    if (!(bits & (1u << i))) acc.x[i] = fmaf(wk[k], v[k].x[i], acc.x[i]);
+            }
         }
     }
 }
@@ -143,30 +161,40 @@ __device__ __forceinline__ void gather_scatter_masked(const SampleMeta mt, const
     const ptrdiff_t o[4] = {(ptrdiff_t)mt.off, (ptrdiff_t)mt.off + csb, (ptrdiff_t)mt.off + row, (ptrdiff_t)mt.off + row + csb};
     const int64_t mc[4] = {cell0, cell0 + 1, cell0 + level_w, cell0 + level_w + 1};
     const float aw[4] = {b.a0, b.a1, b.a2, b.a3};
-    unsigned bits[4];
+    unsigned any = 0u;
     C v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        bits[k] = 0xfu;
         v[k] = zero_chunk<C>();
         if (cm & (1u << k)) {
-            bits[k] = lane_mask_bits<4>(m0 + mc[k] * mrow, mcol);
+            any |= lane_mask_any<4>(m0 + mc[k] * mrow, mcol);
             v[k] = C::load(p0 + o[k]);
         }
     }
     float dk[4];
+    if (any == 0u) {   // the common case: no padding under any corner
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 4; ++k) {
+            dk[k] = dot_chunk(g, v[k]);
+            if (cm & (1u << k)) gr.red(gp0 + GS * o[k], aw[k]);
+        }
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (bits[k] & (1u << i)) v[k].x[i] = 0.f;
-        dk[k] = dot_chunk(g, v[k]);
-        if (bits[k] != 0xfu) {
-            RedView<VT> gm = gr;
+        for (int k = 0; k < 4; ++k) {
+            dk[k] = 0.f;
+            if (!(cm & (1u << k))) continue;
+            const unsigned bits = lane_mask_bits<4>(m0 + mc[k] * mrow, mcol);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (bits[k] & (1u << i)) gm.x[i] = 0.f;
-            gm.red(gp0 + GS * o[k], aw[k]);
+                if (bits & (1u << i)) v[k].x[i] = 0.f;
+            dk[k] = dot_chunk(g, v[k]);
+            if (bits != 0xfu) {
+                RedView<VT> gm = gr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (bits & (1u << i)) gm.x[i] = 0.f;
+                gm.red(gp0 + GS * o[k], aw[k]);
+            }
         }
     }
     pa = fmaf(b.w0, dk[0], fmaf(b.w1, dk[1], fmaf(b.w2, dk[2], fmaf(b.w3, dk[3], pa))));

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--train", action="store_true")
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-fused-tails", action="store_true")
     args = ap.parse_args()
     import snipper_b200
     from snipper_b200.harness.snipper_net import build_snipper
@@ -43,6 +44,8 @@ def main():
     torch.manual_seed(42)
     model = build_snipper(snipper_b200.MSDeformAttn).to(dev)
     model.train(args.train)
+    if not args.no_fused_tails:
+        snipper_b200.enable_fused_layer_tails(model)
     x = torch.rand(args.batch, 12, 600, 800, device=dev)
 
     def step():
