@@ -248,6 +248,25 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
                                     0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, DET, ws_ptr, ws_bytes, st)
         assert r == 0, r
 
+    fullmask = pix[..., None].expand(N, T2, S, M * D).contiguous()   # the reference's materialised (N,T,S,C) mask
+    keep = keep + (fullmask,)
+
+    def masked(fn_name, mask, mrs, mcs):
+        def run():
+            if fn_name == "fwd":
+                r = L.msda_snippet_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                           logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
+                                           Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, None, mask.data_ptr(), mrs, mcs,
+                                           dt, 0, st)
+            else:
+                r = L.msda_snippet_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                            logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(),
+                                            goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
+                                            0, 0, rs[0], rs[1], 0, 0, None, None, None, mask.data_ptr(), mrs, mcs,
+                                            dt, 0, None, 0, st)
+            assert r == 0, r
+        return run
+
     def layer_fwd_pre():
         fsum()
         fwd_pre()
@@ -268,6 +287,11 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
              "layer_bwd_presummed(scatter+unsum)": (layer_bwd_pre, bwd_b)}
     if not bf16:
         extra["bwd_presummed_deterministic"] = (bwd_pre_det, bwd_b)
+    if Lq <= 1024:   # the few-queries (decoder) launches are the ones that take the mask inside the gather
+        extra["fwd_direct_pixel_mask"] = (masked("fwd", pix, 1, 0), fwd_b)
+        extra["fwd_direct_channel_mask"] = (masked("fwd", fullmask, M * D, 1), fwd_b)
+        extra["bwd_direct_pixel_mask"] = (masked("bwd", pix, 1, 0), bwd_b)
+        extra["bwd_direct_channel_mask"] = (masked("bwd", fullmask, M * D, 1), bwd_b)
     return fwd, bwd, fwd_b, bwd_b, keep, extra
 
 

@@ -85,11 +85,8 @@ def main():
         loss = step(i)
     e.record()
     barrier()
-    ms = s.elapsed_time(e)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    from snipper_b200 import sharding
+    ms = sharding.max_over_ranks(s.elapsed_time(e), dev)
     # MSDA share: events around our launches, two extra steps
     ops.STATS.reset()
     ops.STATS.timing = True
