@@ -189,6 +189,9 @@ def kernel_table(per_kernel, steps, bf16):
             samples = N * T1 * Lq * M * L * P
             v = min(N * T2 * S * M * D, 4 * samples * D * 3)
             nbytes = e * (v + N * T1 * Lq * M * D) + 4 * (v + 6 * samples)
+        elif tag in ("frame_sum_planar", "frame_unsum_planar"):   # T2 frames on one side, planar slots (4/3 the bytes) on the other
+            N, T2, T1, S, C = dims
+            nbytes = e * N * S * C * T2 + 4 * N * S * (C + C // 3) * (min(T1, T2) + (1 if T1 > T2 else 0))
         elif tag == "frame_sum":          # reads T2 frames, writes one slot per query frame
             N, T2, T1, S, C = dims
             nbytes = e * N * S * C * (T2 + min(T1, T2) + (1 if T1 > T2 else 0))
@@ -196,8 +199,8 @@ def kernel_table(per_kernel, steps, bf16):
             N, T2, T1, S, C = dims
             nbytes = N * S * C * (4 * (min(T1, T2) + (1 if T1 > T2 else 0)) + e * T2)
         elif tag == "layer_tail":          # reads y + residual (+ pos), writes out (+ out + pos); fp32
-            rows, C, with_pos = dims
-            nbytes = 4 * rows * C * (3 + 2 * with_pos)
+            n_rows, C, with_pos = dims
+            nbytes = 4 * n_rows * C * (3 + 2 * with_pos)
         rows.append({"kernel": tag, "dims": "x".join(map(str, dims)), "launches_per_step": len(ms) / steps,
                      "avg_us": round(avg * 1e3, 2), "ms_per_step": round(sum(ms) / steps, 4),
                      "algorithmic_MB": None if nbytes is None else round(nbytes / 1e6, 2),
@@ -209,7 +212,7 @@ def source_fingerprint():
     """Hash of the kernel sources: profiles/roofline_traffic.json is only quoted while it matches."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("msda_snippet.cu", "msda_fast.cuh", "msda_common.cuh", "msda_frames.cu"):
+    for f in ("msda_snippet.cu", "msda_snippet_common.cuh", "msda_planar.cu", "msda_fast.cuh", "msda_common.cuh", "msda_frames.cu"):
         with open(os.path.join(ROOT, "snipper_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -510,7 +513,8 @@ def main():
     e_bytes = 2 if bf16 else 4
     alg_bytes = fused_layer_bytes(dom_dims, e=e_bytes)
     achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
-    presummed = dom_tag.endswith("presummed")
+    planar = dom_tag.endswith("planar")
+    presummed = dom_tag.endswith("presummed") or planar
     # bytes that cross the L1 data pipe: 4 corners x D channels per sample and GATHERED frame (one per query frame
     # when the neighbour frames are pre-summed, |nb(t1)| otherwise)
     N_, T2_, T1_, S_, M_, D_, L_, Lq_, P_ = dom_dims
@@ -522,7 +526,8 @@ def main():
                "gathered_bytes_per_launch": gathered, "achieved_TBps": gathered / (dom_avg_ms * 1e-3) / 1e12,
                "measured_ceiling_TBps": ceiling,
                "frac": (gathered / (dom_avg_ms * 1e-3) / 1e12 / ceiling) if ceiling else None}
-    traffic, traffic_src = recorded_traffic("snippet_forward_presummed_encoder_dram_bytes_per_launch" if presummed
+    traffic, traffic_src = recorded_traffic("snippet_forward_planar_encoder_dram_bytes_per_launch" if planar else
+                                            "snippet_forward_presummed_encoder_dram_bytes_per_launch" if presummed
                                             else "snippet_forward_encoder_dram_bytes_per_launch")
 
     graphed = runner is not None
@@ -557,8 +562,10 @@ def main():
                 "ms_per_step": ms_e2e_total / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "msda_snippet_fwd_kernel<float,12,16,1536,%s> (%s %s)" % (
-                         "presummed" if presummed else "direct", dom_tag, "x".join(map(str, dom_dims))),
+        "roofline": {"bound": "hbm", "kernel": "%s (%s %s)" % (
+                         "msda_planar_fwd_kernel<32>" if planar else
+                         "msda_snippet_fwd_kernel<float,12,16,1536,%s>" % ("presummed" if presummed else "direct"),
+                         dom_tag, "x".join(map(str, dom_dims))),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,

@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 3
+#define MSDA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MSDA_API __attribute__((visibility("default")))
@@ -84,6 +84,14 @@ typedef enum {
 #define MSDA_FLAG_PRESUMMED 4u       /* snippet entries: `value` / `grad_value` hold one neighbour-frame
                                         SUM per query-frame slot, (N, msda_snippet_num_slots(), S, M, D),
                                         as written by msda_frame_sum / consumed by msda_frame_unsum    */
+
+#define MSDA_FLAG_PLANAR 8u          /* with MSDA_FLAG_PRESUMMED: the slots are in the library's PLANAR layout
+                                        (msda_planar_slot_bytes() bytes per (n, slot), 128-byte aligned), as
+                                        written by msda_frame_sum_planar / consumed by msda_frame_unsum_planar.
+                                        The slots are a buffer the library defines, so it lays them out for the
+                                        gather: every L1 wavefront of the encoder kernels is a full 128-byte line
+                                        (6 per sample instead of 8.4, csrc/msda_planar.cu).  MSDA_DTYPE_F32,
+                                        channels == 48; not with MSDA_FLAG_DETERMINISTIC                        */
 
 MSDA_API int msda_abi_version(void);
 MSDA_API const char *msda_error_string(int status);
@@ -132,7 +140,8 @@ MSDA_API int msda_masked_zero(void *data, const unsigned char *mask, int64_t n_e
 /*
  * Fused Snipper snippet attention (one launch per transformer layer).
  *   value            (N,T2,S,M,D)       element strides value_stride_n / value_stride_t
- *                                       [MSDA_FLAG_PRESUMMED: (N,slots,S,M,D), see msda_frame_sum]
+ *                                       [MSDA_FLAG_PRESUMMED: (N,slots,S,M,D), see msda_frame_sum;
+ *                                        with MSDA_FLAG_PLANAR the planar slots of msda_frame_sum_planar]
  *   offsets          (N,T1,Lq,M,L,P,2)  raw sampling_offsets Linear output, in pixels
  *   logits           (N,T1,Lq,M,L,P)    raw attention_weights Linear output
  *                                       both dense per (n,t1,q) row; offsets_row_stride / logits_row_stride =
@@ -175,7 +184,8 @@ MSDA_API int msda_snippet_forward(const void *value, const int64_t *spatial_shap
                          int dtype, unsigned flags, void *stream);
 
 /*
- * grad_value (N,T2,S,M,D contiguous fp32 [MSDA_FLAG_PRESUMMED: (N,slots,S,M,D)]; zero-filled unless
+ * grad_value (N,T2,S,M,D contiguous fp32 [MSDA_FLAG_PRESUMMED: (N,slots,S,M,D); + MSDA_FLAG_PLANAR: planar
+ * fp32 slots, batch * slots * msda_planar_slot_bytes() bytes]; zero-filled unless
  * MSDA_FLAG_ACCUMULATE_VALUE), grad_offsets like offsets, grad_logits like logits (same row strides).
  * The gradient w.r.t. reference_points is sum_{m,p} grad_offsets * (W_l,H_l), the gradients of the biases
  * are the sums of grad_offsets / grad_logits over rows; both are left to the caller.
@@ -228,6 +238,24 @@ MSDA_API int msda_frame_unsum(const void *grad_vsum, const unsigned char *value_
                               int batch, int n_src_frames, int n_query_frames, int n_frame,
                               int spatial_size, int row_elems,
                               int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream);
+
+/*
+ * Planar slots (MSDA_FLAG_PLANAR).  msda_planar_slot_bytes: bytes of one (n, slot) -- allocate
+ * batch * msda_snippet_num_slots() * that, 128-byte aligned -- or 0 when the layout does not apply (then use
+ * msda_frame_sum / msda_frame_unsum and MSDA_FLAG_PRESUMMED alone).  The two passes mirror msda_frame_sum /
+ * msda_frame_unsum (same slots, same mask semantics, same fixed summation order); value and grad_value keep the
+ * reference layout (N,T2,S,M,D), fp32.
+ */
+MSDA_API size_t msda_planar_slot_bytes(int spatial_size, int num_heads, int channels, int dtype);
+MSDA_API int msda_frame_sum_planar(const void *value, const unsigned char *value_mask, void *vsum_planar,
+                                   int batch, int n_src_frames, int n_query_frames, int n_frame,
+                                   int spatial_size, int num_heads, int channels,
+                                   int64_t value_stride_n, int64_t value_stride_t,
+                                   int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream);
+MSDA_API int msda_frame_unsum_planar(const void *grad_vsum_planar, const unsigned char *value_mask, void *grad_value,
+                                     int batch, int n_src_frames, int n_query_frames, int n_frame,
+                                     int spatial_size, int num_heads, int channels,
+                                     int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream);
 
 /*
  * Layer tail: what follows every attention / FFN block of the reference's encoder and

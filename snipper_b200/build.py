@@ -9,8 +9,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmsda_b200.so")
-SOURCES = ["msda_capi.cu", "msda_percall.cu", "msda_snippet.cu", "msda_deterministic.cu", "msda_mask.cu", "msda_frames.cu", "msda_tail.cu"]
-HEADERS = ["msda_common.cuh", "msda_fast.cuh", "msda_internal.h", os.path.join("..", "..", "include", "msda_b200.h")]
+SOURCES = ["msda_capi.cu", "msda_percall.cu", "msda_snippet.cu", "msda_deterministic.cu", "msda_mask.cu", "msda_frames.cu", "msda_tail.cu", "msda_planar.cu"]
+HEADERS = ["msda_common.cuh", "msda_fast.cuh", "msda_snippet_common.cuh", "msda_internal.h", os.path.join("..", "..", "include", "msda_b200.h")]
 OBJ_DIR = os.path.join(PKG, "lib", "obj")
 
 NVCC_FLAGS = [

@@ -8,7 +8,7 @@ import os
 
 from .build import LIB_PATH
 
-MSDA_ABI_VERSION = 3
+MSDA_ABI_VERSION = 4
 
 MSDA_OK = 0
 MSDA_ERR_INVALID_ARGUMENT = 1
@@ -25,13 +25,14 @@ MSDA_DTYPE_BF16 = 2
 MSDA_FLAG_DETERMINISTIC = 1
 MSDA_FLAG_ACCUMULATE_VALUE = 2
 MSDA_FLAG_PRESUMMED = 4
+MSDA_FLAG_PLANAR = 8
 
 # every symbol include/msda_b200.h declares
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_last_cuda_error", "msda_forward",
     "msda_backward", "msda_backward_workspace_bytes", "msda_masked_zero", "msda_snippet_forward",
     "msda_snippet_backward", "msda_snippet_backward_workspace_bytes", "msda_snippet_num_slots", "msda_snippet_prefers_presum", "msda_frame_sum",
-    "msda_frame_unsum", "msda_layer_tail",
+    "msda_frame_unsum", "msda_layer_tail", "msda_planar_slot_bytes", "msda_frame_sum_planar", "msda_frame_unsum_planar",
 )
 
 _lib = None
@@ -83,6 +84,12 @@ def lib():
     L.msda_frame_sum.argtypes = [vp, vp, vp] + [i32] * 6 + [i64, i64, i64, i32, i32, vp]
     L.msda_frame_unsum.restype = i32
     L.msda_frame_unsum.argtypes = [vp, vp, vp] + [i32] * 6 + [i64, i32, i32, vp]
+    L.msda_planar_slot_bytes.restype = sz
+    L.msda_planar_slot_bytes.argtypes = [i32] * 4
+    L.msda_frame_sum_planar.restype = i32
+    L.msda_frame_sum_planar.argtypes = [vp, vp, vp] + [i32] * 7 + [i64, i64, i64, i32, i32, vp]
+    L.msda_frame_unsum_planar.restype = i32
+    L.msda_frame_unsum_planar.argtypes = [vp, vp, vp] + [i32] * 7 + [i64, i32, i32, vp]
     L.msda_layer_tail.restype = i32
     L.msda_layer_tail.argtypes = [vp] * 8 + [i64, i32, ctypes.c_float, i32, vp]
     if L.msda_abi_version() != MSDA_ABI_VERSION:

@@ -277,7 +277,11 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
                          const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                          int dtype, unsigned flags, void *stream)
 {
-    if (flags & ~MSDA_FLAG_PRESUMMED) return MSDA_ERR_INVALID_ARGUMENT;
+    if (flags & ~(MSDA_FLAG_PRESUMMED | MSDA_FLAG_PLANAR)) return MSDA_ERR_INVALID_ARGUMENT;
+    const bool planar = (flags & MSDA_FLAG_PLANAR) != 0;
+    if (planar && !(flags & MSDA_FLAG_PRESUMMED)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (planar && (dtype != MSDA_DTYPE_F32 || msda::planar_slot_bytes(spatial_size, num_heads, channels, 4) == 0))
+        return MSDA_ERR_UNSUPPORTED_DTYPE;
     msda::SnippetDims d;
     int st = snippet_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads,
                           channels, num_levels, num_query, num_point, value_stride_n,
@@ -292,6 +296,12 @@ int msda_snippet_forward(const void *value, const int64_t *spatial_shapes,
     if (!aligned16(value) || !aligned16(output) || (reinterpret_cast<uintptr_t>(offsets) & 7u) ||
         (reinterpret_cast<uintptr_t>(logits) & 3u) || (reinterpret_cast<uintptr_t>(offsets_bias) & 7u))
         return MSDA_ERR_INVALID_ARGUMENT;
+    if (planar) {
+        if (reinterpret_cast<uintptr_t>(value) & 127u) return MSDA_ERR_INVALID_ARGUMENT;
+        return cuda_status(msda::launch_planar_forward_f32(
+            value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
+            (const float *)reference_points, (float *)output, d, static_cast<cudaStream_t>(stream)));
+    }
     if (dtype == MSDA_DTYPE_BF16)
         return cuda_status(msda::launch_snippet_forward_bf16(
             value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
@@ -316,8 +326,13 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
                           const unsigned char *value_mask, int64_t mask_row_stride, int mask_col_stride,
                           int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *stream)
 {
-    if (flags & ~(MSDA_FLAG_PRESUMMED | MSDA_FLAG_ACCUMULATE_VALUE | MSDA_FLAG_DETERMINISTIC)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (flags & ~(MSDA_FLAG_PRESUMMED | MSDA_FLAG_ACCUMULATE_VALUE | MSDA_FLAG_DETERMINISTIC | MSDA_FLAG_PLANAR))
+        return MSDA_ERR_INVALID_ARGUMENT;
     const bool deterministic = (flags & MSDA_FLAG_DETERMINISTIC) != 0;
+    const bool planar = (flags & MSDA_FLAG_PLANAR) != 0;
+    if (planar && (deterministic || !(flags & MSDA_FLAG_PRESUMMED))) return MSDA_ERR_INVALID_ARGUMENT;
+    if (planar && (dtype != MSDA_DTYPE_F32 || msda::planar_slot_bytes(spatial_size, num_heads, channels, 4) == 0))
+        return MSDA_ERR_UNSUPPORTED_DTYPE;
     // deterministic mode: two-pass grad_value over the pre-summed slots, float32
     if (deterministic && !(flags & MSDA_FLAG_PRESUMMED)) return MSDA_ERR_INVALID_ARGUMENT;
     if (deterministic && dtype != MSDA_DTYPE_F32) return MSDA_ERR_UNSUPPORTED_DTYPE;
@@ -331,7 +346,8 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
     if (!reference_points && encoder_valid_ratios) reference_points = encoder_valid_ratios;  // never dereferenced; passes the null checks
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int gframes = (flags & MSDA_FLAG_PRESUMMED) ? msda::snippet_num_slots(n_query_frames, n_frame) : n_src_frames;
-    const size_t value_elems = (size_t)batch * gframes * spatial_size * num_heads * channels;
+    const size_t value_elems = planar ? (size_t)batch * gframes * (msda::planar_slot_bytes(spatial_size, num_heads, channels, 4) / 4)
+                                      : (size_t)batch * gframes * spatial_size * num_heads * channels;
     if (deterministic) {
         // 32-bit corner / cell ids (checked before anything is enqueued)
         const int64_t samples = (int64_t)batch * n_query_frames * num_query * num_heads * num_levels * num_point;
@@ -384,6 +400,14 @@ int msda_snippet_backward(const void *value, const int64_t *spatial_shapes,
         (reinterpret_cast<uintptr_t>(offsets) & 7u) || (reinterpret_cast<uintptr_t>(grad_offsets) & 7u) ||
         (reinterpret_cast<uintptr_t>(offsets_bias) & 7u))
         return MSDA_ERR_INVALID_ARGUMENT;
+    if (planar) {
+        if ((reinterpret_cast<uintptr_t>(value) & 127u) || (reinterpret_cast<uintptr_t>(grad_value) & 127u))
+            return MSDA_ERR_INVALID_ARGUMENT;
+        return cuda_status(msda::launch_planar_backward_f32(
+            value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
+            (const float *)reference_points, (const float *)grad_output, grad_value, (float *)grad_offsets,
+            (float *)grad_logits, d, s));
+    }
     if (dtype == MSDA_DTYPE_BF16)
         return cuda_status(msda::launch_snippet_backward_bf16(
             value, spatial_shapes, level_start_index, (const float *)offsets, (const float *)logits,
@@ -485,6 +509,52 @@ int msda_frame_unsum(const void *grad_vsum, const unsigned char *value_mask, voi
     if (dtype == MSDA_DTYPE_F32 && !aligned16(grad_value)) return MSDA_ERR_INVALID_ARGUMENT;
     return cuda_status(msda::launch_frame_unsum(static_cast<const float *>(grad_vsum), value_mask, grad_value, d,
                                                 dtype == MSDA_DTYPE_BF16 ? 2 : 4, static_cast<cudaStream_t>(stream)));
+}
+
+size_t msda_planar_slot_bytes(int spatial_size, int num_heads, int channels, int dtype)
+{
+    if (dtype != MSDA_DTYPE_F32) return 0;
+    return msda::planar_slot_bytes(spatial_size, num_heads, channels, 4);
+}
+
+int msda_frame_sum_planar(const void *value, const unsigned char *value_mask, void *vsum_planar,
+                          int batch, int n_src_frames, int n_query_frames, int n_frame,
+                          int spatial_size, int num_heads, int channels, int64_t value_stride_n, int64_t value_stride_t,
+                          int64_t mask_row_stride, int mask_col_stride, int dtype, void *stream)
+{
+    if (dtype != MSDA_DTYPE_F32 || num_heads <= 0 || channels <= 0 ||
+        msda::planar_slot_bytes(spatial_size, num_heads, channels, 4) == 0)
+        return MSDA_ERR_UNSUPPORTED_DTYPE;
+    msda::FrameDims d;
+    int st = frame_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads * channels,
+                        value_stride_n, value_stride_t, value_mask, mask_row_stride, mask_col_stride, dtype);
+    if (st != MSDA_OK) return st;
+    if (!msda::frame_dims_ok(d, 4)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (batch == 0) return MSDA_OK;
+    if (!value || !vsum_planar || !aligned16(value) || (reinterpret_cast<uintptr_t>(vsum_planar) & 127u))
+        return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_frame_sum_planar(static_cast<const float *>(value), value_mask, vsum_planar, d,
+                                                     num_heads, static_cast<cudaStream_t>(stream)));
+}
+
+int msda_frame_unsum_planar(const void *grad_vsum_planar, const unsigned char *value_mask, void *grad_value,
+                            int batch, int n_src_frames, int n_query_frames, int n_frame,
+                            int spatial_size, int num_heads, int channels, int64_t mask_row_stride, int mask_col_stride,
+                            int dtype, void *stream)
+{
+    if (dtype != MSDA_DTYPE_F32 || num_heads <= 0 || channels <= 0 ||
+        msda::planar_slot_bytes(spatial_size, num_heads, channels, 4) == 0)
+        return MSDA_ERR_UNSUPPORTED_DTYPE;
+    msda::FrameDims d;
+    int st = frame_dims(d, batch, n_src_frames, n_query_frames, n_frame, spatial_size, num_heads * channels, 0, 0,
+                        value_mask, mask_row_stride, mask_col_stride, dtype);
+    if (st != MSDA_OK) return st;
+    if (!msda::frame_dims_ok(d, 4)) return MSDA_ERR_INVALID_ARGUMENT;
+    if (batch == 0) return MSDA_OK;
+    if (!grad_vsum_planar || !grad_value || (reinterpret_cast<uintptr_t>(grad_vsum_planar) & 127u) || !aligned16(grad_value))
+        return MSDA_ERR_INVALID_ARGUMENT;
+    return cuda_status(msda::launch_frame_unsum_planar(grad_vsum_planar, value_mask, static_cast<float *>(grad_value), d,
+                                                       num_heads, static_cast<cudaStream_t>(stream)));
 }
 
 int msda_layer_tail(const void *y, const void *bias, const void *residual, const void *gamma, const void *beta,

@@ -114,6 +114,20 @@ cudaError_t launch_frame_sum(const void *value, const uint8_t *mask, void *vsum,
 cudaError_t launch_frame_unsum(const float *grad_vsum, const uint8_t *mask, void *grad_value, const FrameDims &d,
                                int out_esize, cudaStream_t stream);
 
+// ---- planar neighbour-frame slots (msda_planar.cu): fp32, D = 48 ----
+// bytes of one (n, slot) of the planar layout, 0 when it does not apply
+size_t planar_slot_bytes(int S, int M, int D, int esize);
+cudaError_t launch_frame_sum_planar(const float *value, const uint8_t *mask, void *vsum, const FrameDims &d, int M,
+                                    cudaStream_t stream);
+cudaError_t launch_frame_unsum_planar(const void *grad_vsum, const uint8_t *mask, float *grad_value, const FrameDims &d,
+                                      int M, cudaStream_t stream);
+cudaError_t launch_planar_forward_f32(const void *vsum, const int64_t *shapes, const int64_t *lsi, const float *offsets,
+                                      const float *logits, const float *ref, float *out, const SnippetDims &d,
+                                      cudaStream_t stream);
+cudaError_t launch_planar_backward_f32(const void *vsum, const int64_t *shapes, const int64_t *lsi, const float *offsets,
+                                       const float *logits, const float *ref, const float *grad_out, void *gsum,
+                                       float *grad_offsets, float *grad_logits, const SnippetDims &d, cudaStream_t stream);
+
 // ---- fused snippet op (msda_snippet.cu) ----
 bool snippet_ok(const SnippetDims &d);             // fp32
 bool snippet_ok(const SnippetDims &d, int esize);

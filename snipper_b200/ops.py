@@ -25,6 +25,16 @@ _DTYPES = {torch.float32: capi.MSDA_DTYPE_F32, torch.float64: capi.MSDA_DTYPE_F6
 _deterministic = False
 
 
+# planar neighbour-frame slots (csrc/msda_planar.cu) wherever the layout applies; SNIPPER_B200_PLANAR=0 in the
+# environment or set_planar_slots(False) keeps the cell-major slots (A/B measurements, tests)
+_planar = __import__("os").environ.get("SNIPPER_B200_PLANAR", "1") != "0"
+
+
+def set_planar_slots(flag: bool) -> None:
+    global _planar
+    _planar = bool(flag)
+
+
 def set_deterministic(flag: bool) -> None:
     """Select the bit-reproducible two-pass backward (north_star: 'deterministic two-pass mode')."""
     global _deterministic
@@ -417,16 +427,39 @@ def num_slots(T1: int, n_frame: int) -> int:
     return (T1 if T1 < n_frame else n_frame) + (1 if T1 > n_frame else 0)
 
 
+def planar_slot_elems(S: int, M: int, D: int, dtype) -> int:
+    """fp32 elements of one (n, slot) of the library's planar slot layout (csrc/msda_planar.cu), 0 when the layout
+    does not apply (it is built for float32 heads of 48 channels)."""
+    if dtype != torch.float32:
+        return 0
+    return capi.lib().msda_planar_slot_bytes(S, M, D, capi.MSDA_DTYPE_F32) // 4
+
+
 def _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref, n_frame,
-                  presummed=False, T2=None, valid_ratios=None):
+                  presummed=False, T2=None, valid_ratios=None, planar_dims=None):
+    """``planar_dims`` = (S, M, D): ``value`` is then a planar carry (N, slots, planar_slot_elems) -- see snippet_attn."""
+    if planar_dims is not None:
+        S_, M_, D_ = planar_dims
+        if (value.dim() != 3 or value.dtype != torch.float32 or not value.is_contiguous() or
+                value.shape[2] != planar_slot_elems(S_, M_, D_, value.dtype) or value.data_ptr() % 128 != 0):
+            raise RuntimeError("planar carry must be a contiguous float32 (N, slots, planar_slot_elems) tensor, 128-byte aligned")
+        vshape = (value.shape[0], value.shape[1], S_, M_, D_)
+    else:
+        vshape = tuple(value.shape)
+    return _check_packed_impl(value, vshape, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref,
+                              n_frame, presummed, T2, valid_ratios, planar_dims is not None)
+
+
+def _check_packed_impl(value, vshape, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, ref, n_frame,
+                       presummed, T2, valid_ratios, planar):
     for t, name in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
                     (proj, "proj")) + (((ref, "reference_points"),) if ref is not None else ()):
         _require_cuda(t, name)
-    if value.dim() != 5 or proj.dim() != 4 or (ref is not None and ref.dim() != 5):
+    if len(vshape) != 5 or proj.dim() != 4 or (ref is not None and ref.dim() != 5):
         raise RuntimeError("expected value (N,T2,S,M,D), proj (N,T1,Lq,3*M*L*P), reference_points (N,T1,Lq,L,2)")
     if (ref is None) == (valid_ratios is None):
         raise RuntimeError("pass either reference_points or (encoder self-attention) valid_ratios")
-    N, F, S, M, D = value.shape
+    N, F, S, M, D = vshape
     L = spatial_shapes.shape[0]
     Np, T1, Lq, W = proj.shape
     if Np != N or W % (3 * M * L) != 0:
@@ -449,7 +482,7 @@ def _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias, 
             raise RuntimeError("biases must be contiguous float32 CUDA tensors of 2*M*L*P / M*L*P elements")
     if presummed:
         if F != num_slots(T1, n_frame) or not value.is_contiguous():
-            raise RuntimeError("presummed value must be a contiguous (N, slots, S, M, D) tensor")
+            raise RuntimeError("presummed value must be a contiguous (N, slots, S, M, D) tensor (or a planar carry)")
     else:
         T2 = F
     if not (0 < n_frame <= T2):
@@ -476,6 +509,27 @@ def _frame_sum(value, mask, mrs, mcs, T1, n_frame):
     return vsum
 
 
+def _frame_sum_planar(value, mask, mrs, mcs, T1, n_frame):
+    """(N,T2,S,M,D) -> planar slots (N, slots, planar_slot_elems): the same sums, laid out for the gather."""
+    N, T2, S, M, D = value.shape
+    sn, st = _value_strides5(value)
+    vsum = torch.empty((N, num_slots(T1, n_frame), planar_slot_elems(S, M, D, value.dtype)), dtype=torch.float32,
+                       device=value.device)
+    with torch.cuda.device(value.device), _Launch("frame_sum_planar", (N, T2, T1, S, M * D), value.device):
+        status = capi.lib().msda_frame_sum_planar(value.data_ptr(), _ptr(mask), vsum.data_ptr(), N, T2, T1, int(n_frame),
+                                                  S, M, D, sn, st, mrs, mcs, _DTYPES[value.dtype], _stream(value.device))
+    capi.check(status, "msda_frame_sum_planar")
+    return vsum
+
+
+def use_planar(S: int, M: int, D: int, dtype) -> bool:
+    """Planar slots whenever the layout applies (fp32, D = 48) and the deterministic mode (which walks cell-major
+    slots) is off; see set_planar_slots."""
+    if not _planar:
+        return False
+    return planar_slot_elems(S, M, D, dtype) > 0 and not (_deterministic and torch.is_grad_enabled())
+
+
 def _ref_args(reference_points, valid_ratios):
     """-> (tensor to keep alive, ref pointer, batch stride, frame stride, valid-ratio pointer)"""
     if reference_points is None:
@@ -495,8 +549,9 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
     ``mask_layout`` accepts) or None; proj (N,T1,Lq,3*M*L*P) = [offsets | logits] without biases;
     ``reference_points`` (N,T1,Lq,L,2), or None with ``valid_ratios`` (N,L,2) for the encoder's self-attention,
     whose reference points the kernel then derives from the query index (deformable_transformer.py:219-232).
-    Returns (out (N,T1,Lq,M*D), carry): carry is the presummed value (N,slots,S,M,D) when ``presum`` -- the
-    only form of value the backward needs -- and an empty tensor otherwise."""
+    Returns (out (N,T1,Lq,M*D), carry): carry is the presummed value when ``presum`` -- the only form of value the
+    backward needs: (N,slots,S,M,D), or the library's planar slots (N,slots,planar_slot_elems) when ``use_planar`` --
+    and an empty tensor otherwise."""
     N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
                                                  logits_bias, reference_points, n_frame, valid_ratios=valid_ratios)
     mask, mrs, mcs = mask_layout(value_mask, N, T2, S, M * D)
@@ -504,7 +559,11 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
     mlp = M * L * P
     out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
     dims = (N, T2, T1, S, M, D, L, Lq, P)
-    if presum:
+    if presum and use_planar(S, M, D, value.dtype):
+        carry = _frame_sum_planar(value, mask, mrs, mcs, T1, n_frame)
+        src, sn, st, kmask, tag = carry, 0, 0, None, "snippet_forward_planar"
+        flags = capi.MSDA_FLAG_PRESUMMED | capi.MSDA_FLAG_PLANAR
+    elif presum:
         carry = _frame_sum(value, mask, mrs, mcs, T1, n_frame)
         src, sn, st, kmask, flags, tag = carry, 0, 0, None, capi.MSDA_FLAG_PRESUMMED, "snippet_forward_presummed"
     else:
@@ -527,6 +586,8 @@ def _(value, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, 
       valid_ratios, n_frame, presum):
     N, T2, S, M, D = value.shape
     out = value.new_empty((N, proj.shape[1], proj.shape[2], M * D))
+    if presum and use_planar(S, M, D, value.dtype):
+        return out, value.new_empty((N, num_slots(proj.shape[1], n_frame), planar_slot_elems(S, M, D, value.dtype)))
     if presum:
         return out, value.new_empty((N, num_slots(proj.shape[1], n_frame), S, M, D))
     return out, value.new_empty((0,))
@@ -537,12 +598,18 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
                           level_start_index: Tensor, proj: Tensor, offsets_bias: Optional[Tensor],
                           logits_bias: Optional[Tensor], reference_points: Optional[Tensor],
                           valid_ratios: Optional[Tensor], grad_output: Tensor,
-                          n_frame: int, presum: bool, n_src_frames: int, deterministic: bool) -> Tuple[Tensor, Tensor]:
+                          n_frame: int, presum: bool, n_src_frames: int, deterministic: bool,
+                          value_dims: Optional[list[int]] = None) -> Tuple[Tensor, Tensor]:
     """Returns (grad_value (N,T2,S,M,D) in value's dtype, grad_proj with proj's layout [grad_offsets | grad_logits]).
-    ``value_or_vsum`` is what the forward carried: the presummed value when ``presum``, else value itself."""
+    ``value_or_vsum`` is what the forward carried: the presummed value when ``presum`` (planar when
+    ``value_dims`` = [S, M, D] is given: the 3-d carry does not say), else value itself."""
+    planar = value_dims is not None
+    if planar and not presum:
+        raise RuntimeError("planar slots exist on the pre-summed path only")
     N, T2, T1, S, M, D, L, Lq, P = _check_packed(value_or_vsum, spatial_shapes, level_start_index, proj,
                                                  offsets_bias, logits_bias, reference_points, n_frame,
-                                                 presummed=presum, T2=n_src_frames, valid_ratios=valid_ratios)
+                                                 presummed=presum, T2=n_src_frames, valid_ratios=valid_ratios,
+                                                 planar_dims=tuple(value_dims) if planar else None)
     _require_cuda(grad_output, "grad_output")
     _require_contiguous(grad_output, "grad_output")
     if grad_output.dtype != value_or_vsum.dtype or grad_output.numel() != N * T1 * Lq * M * D:
@@ -554,8 +621,26 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
     grad_proj = torch.empty_like(proj)
     dims = (N, T2, T1, S, M, D, L, Lq, P)
     L_ = capi.lib()
-    if deterministic and not (presum and dt == torch.float32):
-        raise RuntimeError("the deterministic fused backward runs on the pre-summed float32 path")
+    if deterministic and not (presum and dt == torch.float32 and not planar):
+        raise RuntimeError("the deterministic fused backward runs on the pre-summed (cell-major) float32 path")
+    if planar:
+        slots = value_or_vsum.shape[1]
+        gsum = torch.empty_like(value_or_vsum)                                       # planar fp32 slots, zero-filled by the call
+        flags = capi.MSDA_FLAG_PRESUMMED | capi.MSDA_FLAG_PLANAR
+        with torch.cuda.device(dev), _Launch("snippet_backward_planar", dims, dev, 2):
+            status = L_.msda_snippet_backward(
+                value_or_vsum.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                proj.data_ptr(), proj.data_ptr() + 4 * 2 * mlp, ref_ptr, grad_output.data_ptr(),
+                gsum.data_ptr(), grad_proj.data_ptr(), grad_proj.data_ptr() + 4 * 2 * mlp,
+                N, T2, T1, int(n_frame), S, M, D, L, Lq, P, 0, 0, rsn, rst, 3 * mlp, 3 * mlp,
+                _ptr(offsets_bias), _ptr(logits_bias), vr_ptr, None, 0, 0, _DTYPES[dt], flags, None, 0, _stream(dev))
+        capi.check(status, "msda_snippet_backward")
+        grad_value = torch.empty((N, T2, S, M, D), dtype=dt, device=dev)
+        with torch.cuda.device(dev), _Launch("frame_unsum_planar", (N, T2, T1, S, M * D), dev):
+            status = L_.msda_frame_unsum_planar(gsum.data_ptr(), _ptr(mask), grad_value.data_ptr(), N, T2, T1, int(n_frame),
+                                                S, M, D, mrs, mcs, _DTYPES[dt], _stream(dev))
+        capi.check(status, "msda_frame_unsum_planar")
+        return grad_value, grad_proj
     if presum:
         slots = value_or_vsum.shape[1]
         gsum = torch.empty((N, slots, S, M, D), dtype=torch.float32, device=dev)   # fp32 accumulation
@@ -599,7 +684,10 @@ def snippet_attn_backward(value_or_vsum: Tensor, value_mask: Optional[Tensor], s
 
 @snippet_attn_backward.register_fake
 def _(value_or_vsum, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias,
-      reference_points, valid_ratios, grad_output, n_frame, presum, n_src_frames, deterministic):
+      reference_points, valid_ratios, grad_output, n_frame, presum, n_src_frames, deterministic, value_dims=None):
+    if value_dims is not None:
+        S, M, D = value_dims
+        return value_or_vsum.new_empty((value_or_vsum.shape[0], n_src_frames, S, M, D)), torch.empty_like(proj)
     N, _, S, M, D = value_or_vsum.shape
     return value_or_vsum.new_empty((N, n_src_frames, S, M, D)), torch.empty_like(proj)
 
@@ -609,6 +697,7 @@ def _attn_setup_context(ctx, inputs, output):
      presum) = inputs
     out, carry = output
     ctx.n_frame, ctx.presum, ctx.T2 = n_frame, bool(presum), value.shape[1]
+    ctx.value_dims = list(value.shape[2:]) if (presum and carry.dim() == 3) else None    # planar carry
     ctx.flags = (reference_points is not None, valid_ratios is not None, ob is not None, lb is not None,
                  value_mask is not None)
     # the presummed value replaces value itself: the backward reads nothing else of it
@@ -624,10 +713,13 @@ def _attn_backward_formula(ctx, grad_output, grad_carry):
     ref, vr, ob, lb, value_mask = [rest.pop(0) if f else None for f in ctx.flags]
     if grad_output is None:
         return (None,) * 11
+    if _deterministic and ctx.value_dims is not None:
+        raise RuntimeError("set_deterministic(True) must be in effect during the forward as well: this graph carried planar "
+                           "slots, which the deterministic two-pass backward does not walk")
     gv, gproj = torch.ops.snipper_b200.snippet_attn_backward(
         value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, ref, vr, grad_output.contiguous(),
-        ctx.n_frame, ctx.presum, ctx.T2, _deterministic)
-    N, _, S, M, D = value.shape
+        ctx.n_frame, ctx.presum, ctx.T2, _deterministic, ctx.value_dims)
+    M = gv.shape[3]
     L = spatial_shapes.shape[0]
     mlp = proj.shape[-1] // 3
     P = mlp // (M * L)

@@ -25,6 +25,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _reset_process_switches():
+    """A failing test must not leave the process-wide switches of snipper_b200.ops flipped for the next one."""
+    yield
+    ops = sys.modules.get("snipper_b200.ops")
+    if ops is not None:
+        ops.set_deterministic(False)
+        ops.set_planar_slots(True)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         return {k: z[k] for k in z.files}

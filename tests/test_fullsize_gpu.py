@@ -72,7 +72,16 @@ def _oracle_run(c, n_frame, dtype):
     return [out.detach(), value.grad, proj.grad, ref.grad, ob.grad, lb.grad]
 
 
-def _ours(c, n_frame, dtype, presum, per_pixel_mask):
+def _ours(c, n_frame, dtype, presum, per_pixel_mask, planar=True):
+    from snipper_b200 import ops
+    ops.set_planar_slots(planar)
+    try:
+        return _ours_run(c, n_frame, dtype, presum, per_pixel_mask)
+    finally:
+        ops.set_planar_slots(True)
+
+
+def _ours_run(c, n_frame, dtype, presum, per_pixel_mask):
     from snipper_b200 import ops
     value = c["value"].detach().to(DEV, dtype).requires_grad_(True)
     proj = c["proj"].to(DEV).requires_grad_(True)
@@ -106,13 +115,14 @@ def _compare(got, want, dtype, pix, presum=False):
 
 
 @pytest.mark.parametrize("N", [1, 2])
-@pytest.mark.parametrize("presum,per_pixel_mask", [(True, False), (True, True), (False, True)])
-def test_encoder_layer_full_size_fp32(N, presum, per_pixel_mask):
+@pytest.mark.parametrize("presum,per_pixel_mask,planar", [(True, False, True), (True, True, True), (True, True, False),
+                                                          (False, True, True)])
+def test_encoder_layer_full_size_fp32(N, presum, per_pixel_mask, planar):
     """The launch `roofline.kernel` names in bench.py (N=1) and the training launch (N=2)."""
     S = sum(h * w for h, w in LEVELS)
     c = _case(N, 4, 4, S, seed=10 + N, encoder=True)
     want = _oracle(c, 4, torch.float32)
-    got = _ours(c, 4, torch.float32, presum, per_pixel_mask)
+    got = _ours(c, 4, torch.float32, presum, per_pixel_mask, planar)
     _compare(got, want, torch.float32, c["pix"])
 
 
@@ -126,12 +136,14 @@ def test_encoder_layer_full_size_bf16(presum):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("presum,per_pixel_mask", [(False, False), (False, True), (True, True)])
-def test_decoder_layer_config3_forecasting(dtype, presum, per_pixel_mask):
-    """BASELINE config 3: T = 4 observed + 2 future query frames, 60 queries, all of `memory` as value."""
+@pytest.mark.parametrize("presum,per_pixel_mask,planar", [(False, False, True), (False, True, True), (True, True, True),
+                                                          (True, True, False)])
+def test_decoder_layer_config3_forecasting(dtype, presum, per_pixel_mask, planar):
+    """BASELINE config 3: T = 4 observed + 2 future query frames, 60 queries, all of `memory` as value.
+    (presum + planar: the all-frames slot of the future query frames in the planar layout.)"""
     c = _case(1, 6, 4, 60, seed=33, encoder=False, sigma_px=6.0)
     want = _oracle(c, 4, dtype)
-    got = _ours(c, 4, dtype, presum, per_pixel_mask)
+    got = _ours(c, 4, dtype, presum, per_pixel_mask, planar)
     _compare(got, want, dtype, c["pix"], presum)
 
 
@@ -185,6 +197,60 @@ def test_presummed_value_is_the_masked_neighbour_sum():
     want_gv = torch.stack([gsum[:, 0] + gsum[:, 1], gsum[:, 0] + gsum[:, 1], gsum[:, 1],
                            torch.zeros_like(gsum[:, 0]), torch.zeros_like(gsum[:, 0])], 1)
     assert rel_err(gv, want_gv) < 1e-6
+
+
+def _planar_decode(buf, N, NS, S, M):
+    """planar slots (N, NS, elems) -> (N, NS, S, M, 48) via plane A + the EVEN copy of plane B, and the odd copy
+    separately (csrc/msda_planar.cu: A [m][s][32], Be [m][s][16], Bo [m][s+1][16], SB = (S + 3) & ~1 cells per head)."""
+    SB = (S + 3) & ~1
+    a_el, b_el = M * S * 32, M * SB * 16
+    A = buf[..., :a_el].view(N, NS, M, S, 32)
+    Be = buf[..., a_el:a_el + b_el].view(N, NS, M, SB, 16)[:, :, :, :S]
+    Bo = buf[..., a_el + b_el:a_el + 2 * b_el].view(N, NS, M, SB, 16)[:, :, :, 1:S + 1]
+    even = torch.cat((A, Be), -1).permute(0, 1, 3, 2, 4)
+    odd = torch.cat((A, Bo), -1).permute(0, 1, 3, 2, 4)
+    return even, odd
+
+
+def test_planar_slots_are_the_masked_neighbour_sums_relaid():
+    """msda_frame_sum_planar / msda_frame_unsum_planar against the torch definitions of the cell-major passes."""
+    from snipper_b200 import capi
+    g = torch.Generator().manual_seed(6)
+    L_ = capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for (N, T2, T1, n_frame, S, M) in ((2, 4, 6, 4, 37, 8), (1, 5, 2, 3, 10, 2), (1, 1, 1, 1, 1, 1)):
+        D, C = 48, M * 48
+        NS = min(T1, n_frame) + (1 if T1 > n_frame else 0)
+        elems = L_.msda_planar_slot_bytes(S, M, D, capi.MSDA_DTYPE_F32) // 4
+        assert elems == M * (S * 32 + ((S + 3) & ~1) * 32)
+        value = torch.randn(N, T2, S, C, generator=g).to(DEV)
+        pix = (torch.rand(N, T2, S, generator=g) < 0.3).to(DEV)
+        full = pix[..., None].expand(N, T2, S, C).contiguous()
+        masked = value.masked_fill(full, 0.0)
+        lo_hi = [(max(j - 1, 0), min(j + 1, n_frame - 1)) for j in range(min(T1, n_frame))] + ([(0, T2 - 1)] if T1 > n_frame else [])
+        want = torch.stack([masked[:, lo:hi + 1].sum(1) for lo, hi in lo_hi], 1).view(N, NS, S, M, D)
+        for mask, mrs, mcs in ((full, C, 1), (pix, 1, 0), (None, 0, 0)):
+            w = want if mask is not None else torch.stack([value[:, lo:hi + 1].sum(1) for lo, hi in lo_hi], 1).view(N, NS, S, M, D)
+            buf = torch.full((N, NS, elems), float("nan"), device=DEV)
+            assert L_.msda_frame_sum_planar(value.data_ptr(), None if mask is None else mask.data_ptr(), buf.data_ptr(),
+                                            N, T2, T1, n_frame, S, M, D, 0, 0, mrs, mcs, capi.MSDA_DTYPE_F32, st) == 0
+            even, odd = _planar_decode(buf, N, NS, S, M)
+            assert rel_err(even, w) < 1e-6 and torch.equal(even, odd)
+            # gradient slots: the two plane-B copies are SUMMED back (the scatter writes either one)
+            gbuf = torch.randn(N, NS, elems, generator=g).to(DEV)
+            ge, go = _planar_decode(gbuf, N, NS, S, M)
+            gslots = torch.cat((ge[..., :32], ge[..., 32:] + go[..., 32:]), -1)                     # (N,NS,S,M,48)
+            gv = torch.full((N, T2, S, C), 7.0, device=DEV)
+            assert L_.msda_frame_unsum_planar(gbuf.data_ptr(), None if mask is None else mask.data_ptr(), gv.data_ptr(),
+                                              N, T2, T1, n_frame, S, M, D, mrs, mcs, capi.MSDA_DTYPE_F32, st) == 0
+            want_gv = torch.stack([sum((gslots[:, j] for j, (lo, hi) in enumerate(lo_hi) if lo <= t <= hi),
+                                       torch.zeros_like(gslots[:, 0])) for t in range(T2)], 1).reshape(N, T2, S, C)
+            if mask is not None:
+                want_gv = want_gv.masked_fill(full, 0.0)
+            assert rel_err(gv, want_gv) < 1e-6
+    # the layout only exists for fp32 heads of 48 channels
+    assert L_.msda_planar_slot_bytes(100, 8, 32, capi.MSDA_DTYPE_F32) == 0
+    assert L_.msda_planar_slot_bytes(100, 8, 48, capi.MSDA_DTYPE_BF16) == 0
 
 
 # ------------------------------------------------------------------- deterministic mode of the fused layer
@@ -253,7 +319,7 @@ def test_module_deterministic_mode_stays_on_the_fused_path():
     finally:
         snipper_b200.set_deterministic(False)
     assert tags == ["frame_sum", "frame_unsum", "snippet_backward_deterministic", "snippet_forward_presummed"], tags
-    assert "snippet_backward_presummed" in tags0
+    assert "snippet_backward_planar" in tags0         # fp32, D = 48: the non-deterministic path runs on planar slots
     for x, y in zip(g1, g2):
         assert torch.equal(x, y)                       # bit-identical run to run
     for x, y in zip(g1, want):

@@ -181,7 +181,10 @@ def test_random_shapes_packed_layer_strategies_and_masks_vs_oracle(seed, dtype):
     want = [want_out.detach()] + [t.grad for t in leaves]
 
     ftol, vtol, stol = (1e-5, 1e-4, 1e-4) if dtype == torch.float32 else (1e-2, 1e-2, 1e-4)
-    for presum in (True, False):
+    # planar slots exist for fp32 D = 48 only; elsewhere the switch changes nothing and the variant is skipped
+    variants = [(True, True), (False, True)] + ([(True, False)] if (D == 48 and dtype == torch.float32) else [])
+    for presum, planar in variants:
+        ops.set_planar_slots(planar)
         for per_pixel in (True, False):
             lv = [t.to(DEV).requires_grad_(True) for t in (value, proj, ob, lb, ref)]
             mask = pix.to(DEV) if per_pixel else pix[..., None].expand(N, T2, S, M * D).contiguous().to(DEV)
@@ -189,7 +192,7 @@ def test_random_shapes_packed_layer_strategies_and_masks_vs_oracle(seed, dtype):
                                         presum=presum)
             out.backward(go.to(DEV))
             got = [out.detach()] + [t.grad for t in lv]
-            tag = (presum, per_pixel)
+            tag = (presum, planar, per_pixel)
             assert rel_err(got[0], want[0]) < ftol, tag
             assert rel_err(got[1], want[1]) < vtol, tag
             # bf16 + pre-summed: the slot sums are themselves stored in bf16, so the fp32 gradients carry bf16-level error
@@ -197,3 +200,67 @@ def test_random_shapes_packed_layer_strategies_and_masks_vs_oracle(seed, dtype):
             for i in (2, 3, 4, 5):
                 assert rel_err(got[i], want[i]) < st, (tag, i)
             assert float(got[1].float().cpu()[pix].abs().max()) == 0.0
+    ops.set_planar_slots(True)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_planar_slots_vs_oracle(seed):
+    """The planar-slot kernels (csrc/msda_planar.cu; fp32, D = 48) on random geometry: odd widths (pairs that start on
+    odd cells read the shifted plane-B copy), one-pixel-wide levels (every sample takes the border path), far offsets,
+    the all-frames slot of future query frames, in-kernel encoder reference points -- against the C oracle composed per
+    (t1,t2), and bit-identical forward between two runs."""
+    from snipper_b200 import ops
+    from snipper_b200.modules import EncoderGrid
+    from snippet_oracle import snippet_attention_oracle
+    rng = random.Random(7000 + seed)
+    L = rng.choice([1, 2, 3, 4])
+    sizes = [(rng.randint(1, 11), rng.randint(1, 11)) for _ in range(L)]
+    shapes = torch.as_tensor(sizes, dtype=torch.long)
+    lsi = level_start_index(shapes)
+    S = int(shapes.prod(1).sum())
+    M, D, P = rng.choice([1, 2, 3, 8]), 48, rng.choice([1, 2, 4, 8])
+    N, n_frame, fut = rng.choice([1, 2]), rng.choice([1, 2, 3, 4]), rng.choice([0, 0, 1, 2])
+    T2 = n_frame + rng.choice([0, 0, 1])
+    T1 = n_frame + fut
+    encoder = seed % 3 == 0                       # queries = pixels, reference points computed in-kernel
+    Lq = S if encoder else rng.choice([1, 7, 40, 65])
+    mlp = M * L * P
+    g = torch.Generator().manual_seed(300 + seed)
+    value = torch.randn(N, T2, S, M, D, generator=g)
+    proj = torch.cat((torch.randn(N, T1, Lq, 2 * mlp, generator=g) * rng.choice([0.5, 2.0, 6.0]),
+                      torch.randn(N, T1, Lq, mlp, generator=g)), -1)
+    ob, lb = torch.randn(2 * mlp, generator=g), torch.randn(mlp, generator=g)
+    pix = torch.rand(N, T2, S, generator=g) < 0.2
+    go = torch.randn(N, T1, Lq, M * D, generator=g)
+    vr = None
+    if encoder:
+        vr = torch.rand(N, L, 2, generator=g) * 0.4 + 0.6
+        ref = EncoderGrid(vr, sizes, T1).tensor().contiguous()
+    else:
+        ref = torch.rand(N, T1, Lq, L, 2, generator=g) * 1.2 - 0.1
+
+    leaves = [t.clone().requires_grad_(True) for t in (value, proj, ob, lb, ref)]
+    want_out = snippet_attention_oracle(leaves[0], pix, shapes, lsi, leaves[1], leaves[2], leaves[3], leaves[4], n_frame)
+    want_out.backward(go)
+    want = [want_out.detach()] + [t.grad for t in leaves]
+
+    outs = []
+    for rep in range(2):
+        ops.STATS.reset()
+        ops.STATS.timing = True
+        lv = [t.to(DEV).requires_grad_(True) for t in (value, proj, ob, lb, ref)]
+        out = ops.snippet_attention(lv[0], pix.to(DEV), shapes.to(DEV), lsi.to(DEV), lv[1], lv[2], lv[3],
+                                    None if encoder else lv[4], n_frame, presum=True,
+                                    valid_ratios=vr.to(DEV) if encoder else None)
+        out.backward(go.to(DEV))
+        ops.STATS.timing = False
+        assert sorted(e[0] for e in ops.STATS.events) == ["frame_sum_planar", "frame_unsum_planar",
+                                                          "snippet_backward_planar", "snippet_forward_planar"]
+        got = [out.detach()] + [t.grad for t in lv]
+        outs.append(got[0])
+        assert rel_err(got[0], want[0]) < 1e-5
+        assert rel_err(got[1], want[1]) < 1e-4
+        for i in (2, 3, 4) + (() if encoder else (5,)):
+            assert rel_err(got[i], want[i]) < 1e-4, i
+        assert float(got[1].cpu()[pix].abs().max()) == 0.0
+    assert torch.equal(outs[0], outs[1])

@@ -267,6 +267,45 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
             assert r == 0, r
         return run
 
+    # planar slots (csrc/msda_planar.cu): the same four passes on the library's own slot layout
+    pl_elems = 0 if bf16 else L.msda_planar_slot_bytes(S, M, D, 0) // 4
+    PLN = PRE | capi.MSDA_FLAG_PLANAR
+    if pl_elems:
+        pvsum = torch.empty(N, slots, pl_elems, device="cuda")
+        pgsum = torch.empty(N, slots, pl_elems, device="cuda")
+        keep = keep + (pvsum, pgsum)
+
+    def fsum_pl():
+        r = L.msda_frame_sum_planar(value.data_ptr(), pix.data_ptr(), pvsum.data_ptr(), N, T2, T1, n_frame, S, M, D, 0, 0,
+                                    1, 0, dt, st)
+        assert r == 0, r
+
+    def fwd_pl():
+        r = L.msda_snippet_forward(pvsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                   logits.data_ptr(), ref.data_ptr(), out.data_ptr(), N, T2, T1, n_frame, S, M, D,
+                                   Lv, Lq, P, 0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, PLN, st)
+        assert r == 0, r
+
+    def bwd_pl():
+        r = L.msda_snippet_backward(pvsum.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), offsets.data_ptr(),
+                                    logits.data_ptr(), ref.data_ptr(), go.data_ptr(), pgsum.data_ptr(),
+                                    goff.data_ptr(), glog.data_ptr(), N, T2, T1, n_frame, S, M, D, Lv, Lq, P,
+                                    0, 0, rs[0], rs[1], 0, 0, None, None, None, None, 0, 0, dt, PLN, None, 0, st)
+        assert r == 0, r
+
+    def funsum_pl():
+        r = L.msda_frame_unsum_planar(pgsum.data_ptr(), pix.data_ptr(), gv2.data_ptr(), N, T2, T1, n_frame, S, M, D,
+                                      1, 0, dt, st)
+        assert r == 0, r
+
+    def layer_fwd_pl():
+        fsum_pl()
+        fwd_pl()
+
+    def layer_bwd_pl():
+        bwd_pl()
+        funsum_pl()
+
     def layer_fwd_pre():
         fsum()
         fwd_pre()
@@ -285,6 +324,11 @@ def snippet_calls(N, T1, T2, Lq, n_frame=4, M=8, D=48, P=4, levels=LEVELS, encod
              "layer_fwd_presummed(sum+gather)": (layer_fwd_pre, fwd_b),
              "bwd_presummed": (bwd_pre, bwd_b), "frame_unsum": (funsum, full * (4 * slots + e * T2)),
              "layer_bwd_presummed(scatter+unsum)": (layer_bwd_pre, bwd_b)}
+    if pl_elems:
+        extra.update({"frame_sum_planar": (fsum_pl, e * full * T2 + 4 * N * slots * pl_elems), "fwd_planar": (fwd_pl, fwd_b),
+                      "layer_fwd_planar(sum+gather)": (layer_fwd_pl, fwd_b), "bwd_planar": (bwd_pl, bwd_b),
+                      "frame_unsum_planar": (funsum_pl, 4 * N * slots * pl_elems + e * full * T2),
+                      "layer_bwd_planar(scatter+unsum)": (layer_bwd_pl, bwd_b)})
     if not bf16:
         extra["bwd_presummed_deterministic"] = (bwd_pre_det, bwd_b)
     if Lq <= 1024:   # the few-queries (decoder) launches are the ones that take the mask inside the gather
@@ -308,6 +352,7 @@ def main():
                     help="also time the per-call kernels on a head-major copy (value (N*M,S,1,D)): what a packed value layout would give")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--inner", type=int, default=10, help="back-to-back launches per timed interval")
+    ap.add_argument("--only", default="", help="comma-separated substrings: time only the fused-layer passes whose name contains one")
     ap.add_argument("--cases", default="snip_enc_N1,snip_dec_N1,enc_N1,enc_N2,enc_N8,dec_N1,dec_N2")
     args = ap.parse_args()
     global WARMUP, INNER
@@ -335,6 +380,12 @@ def main():
             hf, hb, hfb, hbb, hkeep, hextra = snippet_calls(N, T1, 4, Lq, encoder=enc, regime=args.regime, bf16=True)
             rows += [("ours_fused_layer_bf16", "fwd_direct", hf, hfb), ("ours_fused_layer_bf16", "bwd_direct", hb, hbb)]
             rows += [("ours_fused_layer_bf16", k, fn, nb) for k, (fn, nb) in hextra.items()]
+        if args.only:
+            # the streaming passes still run once so that the gathers they feed see real data
+            for impl, which, fn, nbytes in rows:
+                if which.startswith("frame_sum"):
+                    fn()
+            rows = [r for r in rows if any(k in r[1] for k in args.only.split(","))]
         for impl, which, fn, nbytes in rows:
             med, best = time_fn(fn, args.iters, args.flush)
             print(json.dumps({"case": name, "impl": impl, "pass": which, "us_median": round(med, 2),
