@@ -42,7 +42,7 @@ def build_library(force=False, verbose=False, extra_flags=()):
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + os.environ.get("MSDA_NVCC_EXTRA", "").split() + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
         res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         return src, obj, res
 

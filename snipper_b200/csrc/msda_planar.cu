@@ -247,6 +247,20 @@ PlanarFrameArgs make_planar_frame_args(const FrameDims &d, int M)
 
 // ------------------------------------------------------------------------------------------
 // gather / scatter kernels: grid = (M, query tiles, N*T1); CTA = PAIRS queries x 8 lanes, one head
+//
+// A query belongs to ONE QUARTER WARP from its first load to its last store, so the kernels need no block-wide
+// barrier after the level table is staged: warps of a CTA drift apart and the set-up loads of one overlap the
+// gathers of another.
+//   phase 1  lane j sets up samples j, j+8, ..: biases, softmax over the query's L*P logits (quarter-warp
+//            shuffles: one expf per sample instead of L*P+1), loc = ref + offset / (W_l, H_l) in the reference's
+//            operation order (ms_deform_attn.py:164-165), bilinear set-up, and parks TWO 16-byte records per sample:
+//              weights  forward: the four corner weights x A;   backward: {lx, ly, A, -}
+//              offsets  {plane-A byte offset of (y0,x0) | corner mask, the same one row down, plane-B offsets of the
+//                        row-y0 / row-y0+1 pairs (already pointing into the even or the odd copy)}
+//            -- everything a lane would otherwise recompute per sample (8 lanes x ~35 instructions) is done once.
+//   phase 2  per sample two broadcast LDS.128, then the loads / reductions.  When all four corners are inside the level
+//            (mask 15, the common case) every offset is non-negative and goes into the address as an unsigned 32-bit
+//            add; the mask bits ride in the low bits of the first offset and are folded into the base pointer.
 // ------------------------------------------------------------------------------------------
 template <int PAIRS>
 struct PlanarCfg {
@@ -254,38 +268,145 @@ struct PlanarCfg {
     static_assert(THREADS % 32 == 0 && THREADS <= 1024, "quarter warps must tile warps");
 };
 
-struct SampleAddr {
-    int a_off;      // byte offset of the (y0,x0) cell in plane A
-    int b0, b1;     // byte offsets of the row-y0 / row-y0+1 pair in plane Be (+ odd_delta when the pair starts on an odd cell)
-    unsigned mask;  // corner validity bits
-};
-
-__device__ __forceinline__ SampleAddr sample_addr(const float4 &r, int level_w, int odd_delta)
+__device__ __forceinline__ float quarter_max(float v)
 {
-    const int om = __float_as_int(r.w);
-    const int off16 = om & ~15;                   // (start + y0*W + x0) * 16, may be negative for border samples
-    const int off16b = off16 + level_w * 16;      // the cell below
-    SampleAddr s;
-    s.mask = (unsigned)(om & 15);
-    s.a_off = off16 * 8;
-    s.b0 = off16 * 4 + ((off16 & 16) ? odd_delta : 0);
-    s.b1 = off16b * 4 + ((off16b & 16) ? odd_delta : 0);
-    return s;
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
 }
 
+__device__ __forceinline__ float quarter_sum(float v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v + __shfl_xor_sync(0xffffffffu, v, 4);
+}
+
+// Encoder self-attention (Lq == S): the queries ARE the pixels of the pyramid, row-major per level.  A CTA's PAIRS
+// consecutive query slots are mapped to a 2-D patch of ONE level (8 wide x PAIRS/8 tall) instead of a row segment,
+// so that the cells its samples touch overlap more and stay in L1 (row segment of 32 pixels, offsets within +-4 px:
+// ~720 cells per head over the three levels; 8 x 4 patch: ~400).  A bijection of [0, S) onto itself per level (bands of
+// TH rows, walked tile by tile; the last tile of a band may be narrower, the last band lower); slots outside every
+// level map to themselves.  Results do not depend on it.
+template <int TH>
+__device__ __forceinline__ int tile_query(int q, const LevelTable &lv, int L)
+{
+    constexpr int TW = 8;
+    int l = 0;
+    while (l + 1 < L && q >= lv.start[l + 1]) ++l;
+    const int W = lv.W[l], H = lv.H[l], r = q - lv.start[l];
+    if (W <= 0 || r < 0 || r >= W * H) return q;
+    const int band = r / (TH * W), k = r - band * TH * W;
+    const int rb = min(TH, H - band * TH);              // rows of this band
+    const int tile = rb * TW, full = (W / TW) * tile;   // pixels of a full-width tile / of all of them
+    int tx, inner, wt;
+    if (k < full) { tx = k / tile; inner = k - tx * tile; wt = TW; }
+    else { tx = W / TW; inner = k - full; wt = W - tx * TW; }
+    const int dy = inner / wt, dx = inner - dy * wt;
+    return lv.start[l] + (band * TH + dy) * W + tx * TW + dx;
+}
+
+// Phase 1 (see above).  Every lane of the warp calls it (full-mask shuffles); `live` = the quarter warp's query exists.
+// recw / reco / zs point at the query's own LP entries.  BWD selects the weight record.
+template <bool BWD>
+__device__ __forceinline__ void planar_phase1(float4 *recw, uint4 *reco, float *zs, const LevelTable &lv,
+                                              const SnipArgs &a, const PlanarGeom &g, int n, int t1, int q, bool live,
+                                              int j, int m, size_t row, const float *__restrict__ offsets,
+                                              const float *__restrict__ logits, const float *__restrict__ ref, float inv_k)
+{
+    const SnippetDims &d = a.d;
+    const int LP = d.L * d.P;
+    float mx = -INFINITY;
+    if (live) {
+        const float *zrow = logits + row * d.logit_row_stride + m * LP;
+        for (int i = j; i < LP; i += 8) {
+            float z = __ldg(zrow + i);
+            if (d.logit_bias != nullptr) z += __ldg(d.logit_bias + m * LP + i);
+            zs[i] = z;
+            mx = fmaxf(mx, z);
+        }
+    }
+    mx = quarter_max(mx);
+    float sum = 0.f;
+    if (live)
+        for (int i = j; i < LP; i += 8) {
+            const float e = expf(zs[i] - mx);
+            zs[i] = e;
+            sum += e;
+        }
+    sum = quarter_sum(sum);
+    if (!live) {   // empty records: the quarter warp walks them and does nothing (the backward's phase 3 reads A = 0)
+        for (int i = j; i < LP; i += 8) { recw[i] = make_float4(0.f, 0.f, 0.f, 0.f); reco[i] = make_uint4(0u, 0u, 0u, 0u); }
+        return;
+    }
+    // encoder: the query is pixel (y, x) of level lq; its reference point on level l is this times vr[l]
+    // (analytic_reference_point, same operations in the same order)
+    float rxb = 0.f, ryb = 0.f;
+    const float *vr = d.valid_ratios ? d.valid_ratios + (size_t)n * d.L * 2 : nullptr;
+    if (vr != nullptr) {
+        int lq = 0;
+        while (lq + 1 < d.L && q >= lv.start[lq + 1]) ++lq;
+        const int Wq = max(lv.W[lq], 1);
+        const int r = q - lv.start[lq];
+        const int y = r / Wq, x = r - y * Wq;
+        rxb = ((float)x + 0.5f) / (__ldg(vr + 2 * lq) * (float)lv.W[lq]);
+        ryb = ((float)y + 0.5f) / (__ldg(vr + 2 * lq + 1) * (float)lv.H[lq]);
+    }
+    const float2 *orow = reinterpret_cast<const float2 *>(offsets + row * d.off_row_stride) + m * LP;
+    for (int i = j; i < LP; i += 8) {
+        const int l = fast_div(i, a.magic_P);
+        float2 o = __ldg(orow + i);
+        if (d.off_bias != nullptr) {
+            const float2 b = __ldg(reinterpret_cast<const float2 *>(d.off_bias) + m * LP + i);
+            o.x += b.x; o.y += b.y;
+        }
+        float2 rp;
+        if (vr != nullptr) {
+            rp = make_float2(rxb * __ldg(vr + 2 * l), ryb * __ldg(vr + 2 * l + 1));
+        } else {
+            const float *p = ref + n * d.ref_stride_n + t1 * d.ref_stride_t + ((int64_t)q * d.L + l) * 2;
+            rp = make_float2(__ldg(p), __ldg(p + 1));
+        }
+        const int W = lv.W[l], H = lv.H[l];
+        const float u = rp.x + o.x / (float)W;
+        const float v = rp.y + o.y / (float)H;
+        const Sample<float> s = make_sample<float>(u, v, H, W, lv.start[l]);
+        const float at = zs[i] / sum * inv_k;
+        if (BWD) {
+            recw[i] = make_float4(s.lx, s.ly, at, 0.f);
+        } else {
+            const float hx = 1.f - s.lx, hy = 1.f - s.ly;
+            const float ah = hy * at, al = s.ly * at;
+            recw[i] = make_float4(ah * hx, ah * s.lx, al * hx, al * s.lx);
+        }
+        const int base = s.base, below = s.base + W;
+        uint4 o4;
+        o4.x = (unsigned)(base * 128) | (unsigned)s.mask;
+        o4.y = (unsigned)(below * 128);
+        o4.z = (unsigned)(base * 64 + ((base & 1) ? g.odd_delta : 0));
+        o4.w = (unsigned)(below * 64 + ((below & 1) ? g.odd_delta : 0));
+        if (s.mask == 0) o4 = make_uint4(0u, 0u, 0u, 0u);
+        reco[i] = o4;
+    }
+}
+
+#ifndef MSDA_PLANAR_FWD_MIN_BLOCKS
+#define MSDA_PLANAR_FWD_MIN_BLOCKS 4     // x 256 threads: register budget 64
+#endif
+
 template <int PAIRS>
-__global__ void __launch_bounds__(PlanarCfg<PAIRS>::THREADS)
+__global__ void __launch_bounds__(PlanarCfg<PAIRS>::THREADS, (MSDA_PLANAR_FWD_MIN_BLOCKS * 256) / PlanarCfg<PAIRS>::THREADS)
 msda_planar_fwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                        const float *__restrict__ offsets, const float *__restrict__ logits, const float *__restrict__ ref,
                        float *__restrict__ out, const SnipArgs a, const PlanarGeom g)
 {
-    using Cfg = PlanarCfg<PAIRS>;
     const SnippetDims &d = a.d;
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
-    float4 *rec = reinterpret_cast<float4 *>(smem_raw);
-    float *zs = reinterpret_cast<float *>(smem_raw + sizeof(float4) * PAIRS * (LP + 1));
+    float4 *recw = reinterpret_cast<float4 *>(smem_raw);
+    uint4 *reco = reinterpret_cast<uint4 *>(smem_raw + sizeof(float4) * PAIRS * LP);
+    float *zs = reinterpret_cast<float *>(smem_raw + 2 * sizeof(float4) * PAIRS * LP);
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * PAIRS;
@@ -293,42 +414,46 @@ msda_planar_fwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
     int lo, hi;
     frame_range(t1, d.n_frame, d.T2, lo, hi);
     const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;
-
-    snippet_phase1<Cfg::THREADS, PAIRS>(rec, zs, lv, shapes, lsi, a, n, t1, q0, m, qbase, offsets, logits, ref,
-                                        1.f / (float)(hi - lo + 1));
-
-    // ---- phase 2: one quarter warp per query ----
     const int pl = tid >> 3, j = tid & 7;
+    const bool live = q0 + pl < d.Lq;
+    recw += pl * LP; reco += pl * LP; zs += pl * LP;
+
+    load_level_table(lv, shapes, lsi, d.L, d.S);
+    __syncthreads();
+    const int q = (a.tile2d && live) ? tile_query<PAIRS / 8>(q0 + pl, lv, d.L) : q0 + pl;
+    planar_phase1<false>(recw, reco, zs, lv, a, g, n, t1, q, live, j, m, qbase + q, offsets, logits, ref,
+                         1.f / (float)(hi - lo + 1));
+    __syncwarp();
+
+    // ---- phase 2 ----
     const bool left = j < kBLanes;                 // plane B: lanes 0-3 hold the x0 cell, lanes 4-7 the x0+1 cell
     const int slot = t1 < d.n_frame ? t1 : a.n_local;
     const char *sp = vsum + ((int64_t)n * a.n_slots + slot) * g.slot_bytes;
     const char *pa = sp + m * g.a_head + 16 * j;
     const char *pb = sp + g.a_bytes + m * g.b_head + 16 * j;
-    const float4 *rr = rec + pl * (LP + 1);
+    const char *pa15 = pa - 15;                    // fast path: offset | 15 == offset + 15
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accb = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int l = 0; l < d.L; ++l) {
-        const int level_w = lv.W[l];
-        const int row = level_w * 128;
+    const int nsamp = live ? LP : 0;
 #pragma unroll 2
-        for (int p = 0; p < d.P; ++p) {
-            const float4 r = rr[l * d.P + p];
-            const SampleAddr s = sample_addr(r, level_w, g.odd_delta);
-            const float4 w = record_weights(r);
-            const float wt = left ? w.x : w.y, wb = left ? w.z : w.w;
-            const char *a0 = pa + s.a_off;
-            if (s.mask == 0xfu) {
-                const float4 v0 = ld16(a0), v1 = ld16(a0 + 128), v2 = ld16(a0 + row), v3 = ld16(a0 + row + 128);
-                const float4 u0 = ld16(pb + s.b0), u1 = ld16(pb + s.b1);
-                fma4(acc, w.x, v0); fma4(acc, w.y, v1); fma4(acc, w.z, v2); fma4(acc, w.w, v3);
-                fma4(accb, wt, u0); fma4(accb, wb, u1);
-            } else if (s.mask != 0u) {
-                if (s.mask & 1u) fma4(acc, w.x, ld16(a0));
-                if (s.mask & 2u) fma4(acc, w.y, ld16(a0 + 128));
-                if (s.mask & 4u) fma4(acc, w.z, ld16(a0 + row));
-                if (s.mask & 8u) fma4(acc, w.w, ld16(a0 + row + 128));
-                if (s.mask & (left ? 1u : 2u)) fma4(accb, wt, ld16(pb + s.b0));
-                if (s.mask & (left ? 4u : 8u)) fma4(accb, wb, ld16(pb + s.b1));
-            }
+    for (int i = 0; i < nsamp; ++i) {
+        const float4 w = recw[i];
+        const uint4 o = reco[i];
+        const float wt = left ? w.x : w.y, wb = left ? w.z : w.w;
+        const unsigned mask = o.x & 15u;
+        if (mask == 0xfu) {
+            const char *a0 = pa15 + o.x, *a1 = pa + o.y;
+            const float4 v0 = ld16(a0), v1 = ld16(a0 + 128), v2 = ld16(a1), v3 = ld16(a1 + 128);
+            const float4 u0 = ld16(pb + o.z), u1 = ld16(pb + o.w);
+            fma4(acc, w.x, v0); fma4(acc, w.y, v1); fma4(acc, w.z, v2); fma4(acc, w.w, v3);
+            fma4(accb, wt, u0); fma4(accb, wb, u1);
+        } else if (mask != 0u) {
+            const char *a0 = pa + (ptrdiff_t)(int)(o.x & ~15u), *a1 = pa + (ptrdiff_t)(int)o.y;
+            if (mask & 1u) fma4(acc, w.x, ld16(a0));
+            if (mask & 2u) fma4(acc, w.y, ld16(a0 + 128));
+            if (mask & 4u) fma4(acc, w.z, ld16(a1));
+            if (mask & 8u) fma4(acc, w.w, ld16(a1 + 128));
+            if (mask & (left ? 1u : 2u)) fma4(accb, wt, ld16(pb + (ptrdiff_t)(int)o.z));
+            if (mask & (left ? 4u : 8u)) fma4(accb, wb, ld16(pb + (ptrdiff_t)(int)o.w));
         }
     }
     // the two halves of the quarter warp hold the same 16 channels of plane B (left / right cells)
@@ -336,8 +461,8 @@ msda_planar_fwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
     accb.y += __shfl_xor_sync(0xffffffffu, accb.y, 4);
     accb.z += __shfl_xor_sync(0xffffffffu, accb.z, 4);
     accb.w += __shfl_xor_sync(0xffffffffu, accb.w, 4);
-    if (q0 + pl < d.Lq) {
-        char *op = reinterpret_cast<char *>(out) + ((qbase + q0 + pl) * d.M + m) * (size_t)(kPlanarD * 4);
+    if (live) {
+        char *op = reinterpret_cast<char *>(out) + ((qbase + q) * d.M + m) * (size_t)(kPlanarD * 4);
         *reinterpret_cast<float4 *>(op + 16 * j) = acc;
         if (left) *reinterpret_cast<float4 *>(op + 128 + 16 * j) = accb;
     }
@@ -373,9 +498,11 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int LP = d.L * d.P;
-    float4 *frac = reinterpret_cast<float4 *>(smem_raw);                                   // {lx, ly, A, off | mask}
-    float *part = reinterpret_cast<float *>(smem_raw + sizeof(float4) * PAIRS * (LP + 1));  // [sample][3]
-    float *zs = part;  // phase-1 scratch aliases `part`
+    float4 *recw_all = reinterpret_cast<float4 *>(smem_raw);                                  // {lx, ly, A, -}
+    uint4 *reco_all = reinterpret_cast<uint4 *>(smem_raw + sizeof(float4) * PAIRS * LP);
+    float *zs_all = reinterpret_cast<float *>(smem_raw + 2 * sizeof(float4) * PAIRS * LP);
+    float *part = zs_all + PAIRS * LP;                                                        // [sample][3]
+    __shared__ int qmap[PAIRS];                                                               // query of each slot of the tile
 
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q0 = blockIdx.y * PAIRS;
@@ -385,14 +512,21 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
     const int nf = hi - lo + 1;
     const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;
 
-    snippet_phase1<Cfg::THREADS, PAIRS>(frac, zs, lv, shapes, lsi, a, n, t1, q0, m, qbase, offsets, logits, ref,
-                                        1.f / (float)nf);
-
-    // ---- phase 2: every thread participates (full-mask shuffles) ----
+    load_level_table(lv, shapes, lsi, d.L, d.S);
+    __syncthreads();
     {
         const int pl = tid >> 3, j = tid & 7;
-        const bool left = j < kBLanes;
         const bool live = q0 + pl < d.Lq;
+        const int q = (a.tile2d && live) ? tile_query<PAIRS / 8>(q0 + pl, lv, d.L) : q0 + pl;
+        if (j == 0) qmap[pl] = q;
+        const bool left = j < kBLanes;
+        float4 *recw = recw_all + pl * LP;
+        uint4 *reco = reco_all + pl * LP;
+        planar_phase1<true>(recw, reco, zs_all + pl * LP, lv, a, g, n, t1, q, live, j, m, qbase + q, offsets, logits, ref,
+                            1.f / (float)nf);
+        __syncwarp();
+
+        // ---- phase 2: every thread participates (full-mask shuffles) ----
         const int slot = t1 < d.n_frame ? t1 : a.n_local;
         const int64_t slot_off = ((int64_t)n * a.n_slots + slot) * g.slot_bytes;
         const char *pa = vsum + slot_off + m * g.a_head + 16 * j;
@@ -401,38 +535,35 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
         char *gb = gsum + slot_off + g.a_bytes + m * g.b_head + 16 * j;
         float4 gA = make_float4(0.f, 0.f, 0.f, 0.f), gB = gA;
         if (live) {
-            const char *gp = reinterpret_cast<const char *>(grad_out) + ((qbase + q0 + pl) * d.M + m) * (size_t)(kPlanarD * 4);
+            const char *gp = reinterpret_cast<const char *>(grad_out) + ((qbase + q) * d.M + m) * (size_t)(kPlanarD * 4);
             gA = ld16(gp + 16 * j);
             gB = ld16(gp + 128 + 16 * (j & 3));
         }
-        const float4 *ff = frac + pl * (LP + 1);
         float *mypart = part + (size_t)(pl * LP) * 3;
-        for (int jj = 0; jj < LP; ++jj) {
-            const float4 f = ff[jj];
-            const int level_w = lv.W[fast_div(jj, a.magic_P)];
-            const int row = level_w * 128;
-            const SampleAddr s = sample_addr(f, level_w, g.odd_delta);
+        for (int i = 0; i < LP; ++i) {
+            const float4 f = recw[i];
+            const uint4 o = reco[i];
+            const unsigned mask = o.x & 15u;
             const BwdWeights bw = make_bwd_weights(f.x, f.y, f.z);
             const float at = left ? bw.a0 : bw.a1, ab = left ? bw.a2 : bw.a3;
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, et = 0.f, eb = 0.f;
-            if (s.mask == 0xfu) {
-                const char *a0 = pa + s.a_off;
-                const float4 v0 = ld16(a0), v1 = ld16(a0 + 128), v2 = ld16(a0 + row), v3 = ld16(a0 + row + 128);
-                const float4 u0 = ld16(pb + s.b0), u1 = ld16(pb + s.b1);
-                char *g0 = ga + s.a_off;
-                red16(g0, bw.a0, gA); red16(g0 + 128, bw.a1, gA); red16(g0 + row, bw.a2, gA); red16(g0 + row + 128, bw.a3, gA);
-                red16(gb + s.b0, at, gB); red16(gb + s.b1, ab, gB);
+            if (mask == 0xfu) {
+                const size_t o0 = (size_t)o.x - 15u, o1 = o.y;
+                const float4 v0 = ld16(pa + o0), v1 = ld16(pa + o0 + 128), v2 = ld16(pa + o1), v3 = ld16(pa + o1 + 128);
+                const float4 u0 = ld16(pb + o.z), u1 = ld16(pb + o.w);
+                red16(ga + o0, bw.a0, gA); red16(ga + o0 + 128, bw.a1, gA); red16(ga + o1, bw.a2, gA); red16(ga + o1 + 128, bw.a3, gA);
+                red16(gb + o.z, at, gB); red16(gb + o.w, ab, gB);
                 d0 = dot4(gA, v0); d1 = dot4(gA, v1); d2 = dot4(gA, v2); d3 = dot4(gA, v3);
                 et = dot4(gB, u0); eb = dot4(gB, u1);
-            } else if (s.mask != 0u) {
-                const char *a0 = pa + s.a_off;
-                char *g0 = ga + s.a_off;
-                if (s.mask & 1u) { d0 = dot4(gA, ld16(a0)); red16(g0, bw.a0, gA); }
-                if (s.mask & 2u) { d1 = dot4(gA, ld16(a0 + 128)); red16(g0 + 128, bw.a1, gA); }
-                if (s.mask & 4u) { d2 = dot4(gA, ld16(a0 + row)); red16(g0 + row, bw.a2, gA); }
-                if (s.mask & 8u) { d3 = dot4(gA, ld16(a0 + row + 128)); red16(g0 + row + 128, bw.a3, gA); }
-                if (s.mask & (left ? 1u : 2u)) { et = dot4(gB, ld16(pb + s.b0)); red16(gb + s.b0, at, gB); }
-                if (s.mask & (left ? 4u : 8u)) { eb = dot4(gB, ld16(pb + s.b1)); red16(gb + s.b1, ab, gB); }
+            } else if (mask != 0u) {
+                const ptrdiff_t o0 = (ptrdiff_t)(int)(o.x & ~15u), o1 = (ptrdiff_t)(int)o.y;
+                const ptrdiff_t b0 = (ptrdiff_t)(int)o.z, b1 = (ptrdiff_t)(int)o.w;
+                if (mask & 1u) { d0 = dot4(gA, ld16(pa + o0)); red16(ga + o0, bw.a0, gA); }
+                if (mask & 2u) { d1 = dot4(gA, ld16(pa + o0 + 128)); red16(ga + o0 + 128, bw.a1, gA); }
+                if (mask & 4u) { d2 = dot4(gA, ld16(pa + o1)); red16(ga + o1, bw.a2, gA); }
+                if (mask & 8u) { d3 = dot4(gA, ld16(pa + o1 + 128)); red16(ga + o1 + 128, bw.a3, gA); }
+                if (mask & (left ? 1u : 2u)) { et = dot4(gB, ld16(pb + b0)); red16(gb + b0, at, gB); }
+                if (mask & (left ? 4u : 8u)) { eb = dot4(gB, ld16(pb + b1)); red16(gb + b1, ab, gB); }
             }
             // this lane's share of d_k = <G, V_k>: its 4 channels of plane A for every corner + its plane-B cell
             if (left) { d0 += et; d2 += eb; } else { d1 += et; d3 += eb; }
@@ -441,8 +572,8 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
             float py_ = fmaf(bw.hx, d2 - d0, bw.lx * (d3 - d1));
             float pax;
             quarter_sum3(pax, py_, pa_, px_, left);
-            if (j == 0) { mypart[jj * 3] = pax; mypart[jj * 3 + 2] = py_; }
-            if (j == 4) mypart[jj * 3 + 1] = pax;
+            if (j == 0) { mypart[i * 3] = pax; mypart[i * 3 + 2] = py_; }
+            if (j == 4) mypart[i * 3 + 1] = pax;
         }
     }
     __syncthreads();
@@ -452,9 +583,9 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
     for (int i = tid; i < PAIRS * LP; i += Cfg::THREADS) {
         const float pa_ = part[i * 3], px_ = part[i * 3 + 1], py_ = part[i * 3 + 2];
         const int spl = fast_div(i, a.magic_LP);
-        const float at = frac[i + spl].z;
+        const float at = recw_all[i].z;
         if (q0 + spl < d.Lq)
-            reinterpret_cast<float2 *>(grad_offsets + (qbase + q0 + spl) * d.off_row_stride)[m * LP + (i - spl * LP)] =
+            reinterpret_cast<float2 *>(grad_offsets + (qbase + qmap[spl]) * d.off_row_stride)[m * LP + (i - spl * LP)] =
                 make_float2(at * px_, at * py_);
         part[i * 3] = pa_ * at;   // own slots only ([0] = gA_i A_i, [1] = gA_i)
         part[i * 3 + 1] = pa_;
@@ -465,8 +596,8 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
         if (q0 + spl < d.Lq) {
             float dot = 0.f;
             for (int jj = 0; jj < LP; ++jj) dot += part[(spl * LP + jj) * 3];
-            grad_logits[(qbase + q0 + spl) * d.logit_row_stride + m * LP + (i - spl * LP)] =
-                frac[i + spl].z * (part[i * 3 + 1] - (float)nf * dot);
+            grad_logits[(qbase + qmap[spl]) * d.logit_row_stride + m * LP + (i - spl * LP)] =
+                recw_all[i].z * (part[i * 3 + 1] - (float)nf * dot);
         }
     }
 }
@@ -474,7 +605,11 @@ msda_planar_bwd_kernel(const char *__restrict__ vsum, const int64_t *__restrict_
 SnipArgs make_planar_args(const SnippetDims &d)
 {
     SnipArgs a = make_snip_args<float>(d);
-    a.cell_bytes = 16;   // records carry (cell index) * 16 | corner mask; the planes scale it by 8 and 4
+    a.cell_bytes = 16;   // (unused by the planar kernels)
+    // encoder self-attention: the query slots of a CTA walk 2-D pixel patches (MSDA_PLANAR_TILE2D=0 in the environment
+    // keeps row segments: benchmark knob, read once; results do not depend on it)
+    static const bool tile2d_on = [] { const char *e = getenv("MSDA_PLANAR_TILE2D"); return !(e && e[0] == '0'); }();
+    a.tile2d = (tile2d_on && d.Lq == d.S) ? 1 : 0;
     return a;
 }
 
@@ -496,7 +631,9 @@ cudaError_t launch_fwd(const void *vsum, const int64_t *shapes, const int64_t *l
     const SnipArgs a = make_planar_args(d);
     const PlanarGeom g = make_geom(d.S, d.M);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = sizeof(float4) * PAIRS * (d.L * d.P + 1) + sizeof(float) * PAIRS * d.L * d.P;
+    const size_t smem = (2 * sizeof(float4) + sizeof(float)) * PAIRS * d.L * d.P;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(msda_planar_fwd_kernel<PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     msda_planar_fwd_kernel<PAIRS><<<grid, PlanarCfg<PAIRS>::THREADS, smem, stream>>>(
         static_cast<const char *>(vsum), shapes, lsi, offsets, logits, ref, out, a, g);
     return cudaGetLastError();
@@ -510,7 +647,7 @@ cudaError_t launch_bwd(const void *vsum, const int64_t *shapes, const int64_t *l
     const SnipArgs a = make_planar_args(d);
     const PlanarGeom g = make_geom(d.S, d.M);
     const dim3 grid(d.M, (d.Lq + PAIRS - 1) / PAIRS, d.N * d.T1);
-    const size_t smem = sizeof(float4) * PAIRS * (d.L * d.P + 1) + sizeof(float) * 3 * PAIRS * d.L * d.P;
+    const size_t smem = (2 * sizeof(float4) + 4 * sizeof(float)) * PAIRS * d.L * d.P;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(msda_planar_bwd_kernel<PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     msda_planar_bwd_kernel<PAIRS><<<grid, PlanarCfg<PAIRS>::THREADS, smem, stream>>>(

@@ -15,6 +15,7 @@ struct SnipArgs {
     int cell_bytes;            // M * D * sizeof(VT)
     unsigned magic_LP, magic_P;
     int n_local, n_slots;      // presummed: slot of query frame t1 = t1 < n_frame ? t1 : n_local
+    int tile2d;                // planar kernels, Lq == S: CTA query slots walk 2-D pixel patches (msda_planar.cu tile_query)
 };
 
 __device__ __forceinline__ void frame_range(int t1, int n_frame, int T2, int &lo, int &hi)
@@ -132,6 +133,7 @@ inline SnipArgs make_snip_args(const SnippetDims &d)
     a.magic_P = fast_magic(d.P);
     a.n_local = d.T1 < d.n_frame ? d.T1 : d.n_frame;
     a.n_slots = snippet_num_slots(d.T1, d.n_frame);
+    a.tile2d = 0;
     return a;
 }
 

@@ -25,9 +25,11 @@ _DTYPES = {torch.float32: capi.MSDA_DTYPE_F32, torch.float64: capi.MSDA_DTYPE_F6
 _deterministic = False
 
 
-# planar neighbour-frame slots (csrc/msda_planar.cu) wherever the layout applies; SNIPPER_B200_PLANAR=0 in the
-# environment or set_planar_slots(False) keeps the cell-major slots (A/B measurements, tests)
-_planar = __import__("os").environ.get("SNIPPER_B200_PLANAR", "1") != "0"
+# planar neighbour-frame slots (csrc/msda_planar.cu): OPT-IN (SNIPPER_B200_PLANAR=1 in the environment or
+# set_planar_slots(True)).  Measured on B200 (profiles/r02_run8_*): full-line L1 wavefronts and 30 % fewer instructions
+# leave the encoder gather where it was (166 vs 164 us) -- both layouts run at the L1 global-load datapath's rate --
+# while the slots take 4/3 of the memory, so the cell-major slots stay the default.
+_planar = __import__("os").environ.get("SNIPPER_B200_PLANAR", "0") == "1"
 
 
 def set_planar_slots(flag: bool) -> None:
@@ -523,8 +525,8 @@ def _frame_sum_planar(value, mask, mrs, mcs, T1, n_frame):
 
 
 def use_planar(S: int, M: int, D: int, dtype) -> bool:
-    """Planar slots whenever the layout applies (fp32, D = 48) and the deterministic mode (which walks cell-major
-    slots) is off; see set_planar_slots."""
+    """Planar slots when opted in (set_planar_slots), the layout applies (fp32, D = 48) and the deterministic mode
+    (which walks cell-major slots) is off."""
     if not _planar:
         return False
     return planar_slot_elems(S, M, D, dtype) > 0 and not (_deterministic and torch.is_grad_enabled())
@@ -542,7 +544,7 @@ def _ref_args(reference_points, valid_ratios):
 def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Tensor, level_start_index: Tensor,
                  proj: Tensor, offsets_bias: Optional[Tensor], logits_bias: Optional[Tensor],
                  reference_points: Optional[Tensor], valid_ratios: Optional[Tensor], n_frame: int,
-                 presum: bool) -> Tuple[Tensor, Tensor]:
+                 presum: bool, planar: bool = False) -> Tuple[Tensor, Tensor]:
     """The whole per-frame loop of the reference module (ms_deform_attn.py:116-117,126-225) for one layer.
 
     value (N,T2,S,M,D) is the raw ``value_proj`` output; ``value_mask`` the padding mask over it (any layout
@@ -550,8 +552,8 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
     ``reference_points`` (N,T1,Lq,L,2), or None with ``valid_ratios`` (N,L,2) for the encoder's self-attention,
     whose reference points the kernel then derives from the query index (deformable_transformer.py:219-232).
     Returns (out (N,T1,Lq,M*D), carry): carry is the presummed value when ``presum`` -- the only form of value the
-    backward needs: (N,slots,S,M,D), or the library's planar slots (N,slots,planar_slot_elems) when ``use_planar`` --
-    and an empty tensor otherwise."""
+    backward needs: (N,slots,S,M,D), or the library's planar slots (N,slots,planar_slot_elems) when ``planar`` (only
+    with ``presum``; ``use_planar`` says where the layout applies) -- and an empty tensor otherwise."""
     N, T2, T1, S, M, D, L, Lq, P = _check_packed(value, spatial_shapes, level_start_index, proj, offsets_bias,
                                                  logits_bias, reference_points, n_frame, valid_ratios=valid_ratios)
     mask, mrs, mcs = mask_layout(value_mask, N, T2, S, M * D)
@@ -559,7 +561,9 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
     mlp = M * L * P
     out = torch.empty((N, T1, Lq, M * D), dtype=value.dtype, device=value.device)
     dims = (N, T2, T1, S, M, D, L, Lq, P)
-    if presum and use_planar(S, M, D, value.dtype):
+    if planar and not (presum and planar_slot_elems(S, M, D, value.dtype) > 0):
+        raise RuntimeError("planar slots need presum=True, float32 value and 48 channels per head")
+    if planar:
         carry = _frame_sum_planar(value, mask, mrs, mcs, T1, n_frame)
         src, sn, st, kmask, tag = carry, 0, 0, None, "snippet_forward_planar"
         flags = capi.MSDA_FLAG_PRESUMMED | capi.MSDA_FLAG_PLANAR
@@ -583,10 +587,10 @@ def snippet_attn(value: Tensor, value_mask: Optional[Tensor], spatial_shapes: Te
 
 @snippet_attn.register_fake
 def _(value, value_mask, spatial_shapes, level_start_index, proj, offsets_bias, logits_bias, reference_points,
-      valid_ratios, n_frame, presum):
+      valid_ratios, n_frame, presum, planar=False):
     N, T2, S, M, D = value.shape
     out = value.new_empty((N, proj.shape[1], proj.shape[2], M * D))
-    if presum and use_planar(S, M, D, value.dtype):
+    if planar:
         return out, value.new_empty((N, num_slots(proj.shape[1], n_frame), planar_slot_elems(S, M, D, value.dtype)))
     if presum:
         return out, value.new_empty((N, num_slots(proj.shape[1], n_frame), S, M, D))
@@ -694,10 +698,10 @@ def _(value_or_vsum, value_mask, spatial_shapes, level_start_index, proj, offset
 
 def _attn_setup_context(ctx, inputs, output):
     (value, value_mask, spatial_shapes, level_start_index, proj, ob, lb, reference_points, valid_ratios, n_frame,
-     presum) = inputs
+     presum, planar) = inputs
     out, carry = output
     ctx.n_frame, ctx.presum, ctx.T2 = n_frame, bool(presum), value.shape[1]
-    ctx.value_dims = list(value.shape[2:]) if (presum and carry.dim() == 3) else None    # planar carry
+    ctx.value_dims = list(value.shape[2:]) if planar else None    # the 3-d planar carry does not say
     ctx.flags = (reference_points is not None, valid_ratios is not None, ob is not None, lb is not None,
                  value_mask is not None)
     # the presummed value replaces value itself: the backward reads nothing else of it
@@ -712,7 +716,7 @@ def _attn_backward_formula(ctx, grad_output, grad_carry):
     rest = saved[4:]
     ref, vr, ob, lb, value_mask = [rest.pop(0) if f else None for f in ctx.flags]
     if grad_output is None:
-        return (None,) * 11
+        return (None,) * 12
     if _deterministic and ctx.value_dims is not None:
         raise RuntimeError("set_deterministic(True) must be in effect during the forward as well: this graph carried planar "
                            "slots, which the deterministic two-pass backward does not walk")
@@ -732,7 +736,7 @@ def _attn_backward_formula(ctx, grad_output, grad_carry):
         goff = gproj[..., :2 * mlp].view(proj.shape[0], proj.shape[1], proj.shape[2], M, L, P, 2)
         wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(goff.dtype)
         gref = (goff * wh[None, None, None, None, :, None, :]).sum(dim=(3, 5))
-    return gv, None, None, None, gproj, gob, glb, gref, None, None, None
+    return gv, None, None, None, gproj, gob, glb, gref, None, None, None, None
 
 
 snippet_attn.register_autograd(_attn_backward_formula, setup_context=_attn_setup_context)
@@ -749,9 +753,11 @@ def snippet_attention(value: Tensor, value_mask: Optional[Tensor], spatial_shape
     L = spatial_shapes.shape[0]
     if presum is None:
         presum = prefers_presum(T2, T1, n_frame, S, L, Lq, W // (3 * M * L)) or (_deterministic and torch.is_grad_enabled())
+    # decided HERE, not inside the op: a custom op body runs with grad mode off
+    planar = bool(presum) and use_planar(S, M, D, value.dtype)
     out, _ = torch.ops.snipper_b200.snippet_attn(value, value_mask, spatial_shapes, level_start_index, proj,
                                                  offsets_bias, logits_bias, reference_points, valid_ratios, n_frame,
-                                                 bool(presum))
+                                                 bool(presum), planar)
     return out
 
 

@@ -32,7 +32,7 @@ def _reset_process_switches():
     ops = sys.modules.get("snipper_b200.ops")
     if ops is not None:
         ops.set_deterministic(False)
-        ops.set_planar_slots(True)
+        ops.set_planar_slots(False)
 
 
 def load_golden(name):

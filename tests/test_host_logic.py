@@ -144,17 +144,14 @@ def test_fake_kernels_give_shapes_without_a_device():
     ref = torch.empty(2, 6, 7, 3, 2, device="meta")
     assert torch.ops.snipper_b200.snippet_forward(v5, sh, lsi, off, lg, ref, 4).shape == (2, 6, 7, 384)
     proj = torch.empty(2, 6, 7, 3 * 8 * 3 * 4, device="meta")
-    from snipper_b200 import ops
-    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, None, 4, True)
+    out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, None, 4, True, True)
     # fp32, D = 48: planar slots (4 frame slots + the all-frames slot), plane A 32 + planes Be / Bo 16 + 16 channels
     assert out.shape == (2, 6, 7, 384) and carry.shape == (2, 5, 8 * (50 * 32 + 52 * 32))
     gv, gp = torch.ops.snipper_b200.snippet_attn_backward(carry, None, sh, lsi, proj, None, None, ref, None, out, 4, True, 4,
                                                           False, [50, 8, 48])
     assert gv.shape == v5.shape and gp.shape == proj.shape
-    ops.set_planar_slots(False)
     out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, None, 4, True)
     assert out.shape == (2, 6, 7, 384) and carry.shape == (2, 5, 50, 8, 48)      # cell-major slots
-    ops.set_planar_slots(True)
     out, carry = torch.ops.snipper_b200.snippet_attn(v5, None, sh, lsi, proj, None, None, ref, None, 4, False)
     assert out.shape == (2, 6, 7, 384) and carry.numel() == 0
     gv, gp = torch.ops.snipper_b200.snippet_attn_backward(v5, None, sh, lsi, proj, None, None, ref, None, out, 4, False, 4,

@@ -1,5 +1,7 @@
-"""Summarise an ncu raw CSV page (ncu -i X.ncu-rep --page raw --csv) into the metrics we track."""
+"""Summarise an ncu capture into the metrics we track: pass a raw CSV page (ncu -i X.ncu-rep --page raw --csv) or the
+.ncu-rep itself (ncu on PATH), optionally a kernel-name substring."""
 import csv
+import subprocess
 import sys
 
 WANT = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
@@ -9,7 +11,11 @@ WANT = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'sm__inst_executed_pipe_lsu.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
-        'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum',
+        'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__m_xbar2l1tex_read_sectors.sum.pct_of_peak_sustained_elapsed',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum',
         'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum',
@@ -26,7 +32,11 @@ WANT = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
 
 
 def main(path, only=None):
-    rows = list(csv.reader(open(path)))
+    if path.endswith(".ncu-rep"):
+        text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rows = list(csv.reader(text.splitlines()))
+    else:
+        rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     for r in rows[2:]:
