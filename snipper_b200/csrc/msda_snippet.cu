@@ -261,6 +261,104 @@ msda_snippet_fwd_kernel(const typename Chunk<VT>::elem *__restrict__ value, cons
     acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
 }
 
+// Few-queries forward (the decoder's cross-attention: 60 queries per frame).  With 16 or 8 queries per CTA such a launch
+// is a few hundred CTAs whose lanes walk L*P samples x |nb(t1)| frames one after the other -- a chain of ~24 dependent
+// round trips to L2 / HBM (58-66 us per launch for 53 MB of traffic, profiles/r02_run9_launch_list_summary.txt).  Here
+// ONE (query, head) pair owns a CTA and thread = (sample, 16-byte chunk): every thread issues the loads of its
+// sample's neighbour frames at once (one round trip), the L*P partial sums meet in shared memory.
+template <int LANES, int BLOCK, int MODE>
+__global__ void __launch_bounds__(BLOCK)
+msda_snippet_fwd_split_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                              const int64_t *__restrict__ lsi, const float *__restrict__ offsets,
+                              const float *__restrict__ logits, const float *__restrict__ ref,
+                              float *__restrict__ out, const SnipArgs a)
+{
+    using C = Chunk<float>;
+    const SnippetDims &d = a.d;
+    __shared__ LevelTable lv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int LP = d.L * d.P;
+    float4 *rec = reinterpret_cast<float4 *>(smem_raw);                    // LP + 1 records
+    float4 *red = rec + (LP + 1);                                          // [sample][chunk] partial sums
+    float *zs = reinterpret_cast<float *>(red + LP * LANES);
+
+    const int tid = threadIdx.x;
+    const int m = blockIdx.x, q = blockIdx.y;
+    const int n = blockIdx.z / d.T1, t1 = blockIdx.z - n * d.T1;
+    int lo, hi;
+    frame_range(t1, d.n_frame, d.T2, lo, hi);
+    const int nf = hi - lo + 1;
+    const size_t qbase = ((size_t)n * d.T1 + t1) * d.Lq;
+
+    snippet_phase1<BLOCK, 1>(rec, zs, lv, shapes, lsi, a, n, t1, q, m, qbase, offsets, logits, ref, 1.f / (float)nf);
+
+    const int sidx = tid / LANES, lane = tid - sidx * LANES;
+    if (sidx < LP) {
+        const char *pf = reinterpret_cast<const char *>(value + n * d.value_stride_n + lo * d.value_stride_t) +
+                         (size_t)(m * LANES + lane) * C::BYTES;
+        const int64_t fstride = d.value_stride_t * (int64_t)sizeof(float);
+        const int level_w = lv.W[fast_div(sidx, a.magic_P)];
+        const float4 r = rec[sidx];
+        C acc = zero_chunk<C>();
+        if (MODE == kDirectMasked) {
+            MaskView mv;
+            mv.row = d.mask_row_stride;
+            mv.frame = (int64_t)d.S * d.mask_row_stride;
+            mv.col = d.mask_col_stride;
+            mv.inv_cell_bytes = 1.f / (float)a.cell_bytes;
+            mv.p = d.mask + ((int64_t)n * d.T2 + lo) * mv.frame + (int64_t)((m * LANES + lane) * C::N) * mv.col;
+            gather_fma_frames_masked<float>(acc, record_meta(r, (unsigned)(level_w * a.cell_bytes)), record_weights(r), pf,
+                                            fstride, nf, a.cell_bytes, level_w, mv);
+        } else {
+            gather_fma_frames<float, 0>(acc, record_meta(r, (unsigned)(level_w * a.cell_bytes)), record_weights(r), pf,
+                                        fstride, nf, a.cell_bytes);
+        }
+        red[sidx * LANES + lane] = make_float4(acc.x[0], acc.x[1], acc.x[2], acc.x[3]);
+    }
+    __syncthreads();
+    if (tid < LANES) {
+        float4 sum = red[tid];
+        for (int j = 1; j < LP; ++j) {       // fixed order: bit-reproducible
+            const float4 v = red[j * LANES + tid];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        const size_t pair = (qbase + q) * d.M + m;
+        *reinterpret_cast<float4 *>(reinterpret_cast<char *>(out) + (pair * LANES + tid) * C::BYTES) = sum;
+    }
+}
+
+// MSDA_FWD_SPLIT=0 in the environment keeps the tile kernels for few-queries launches (benchmark knob, read once)
+static bool fwd_split_on()
+{
+    static const bool v = [] { const char *e = getenv("MSDA_FWD_SPLIT"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+template <int LANES>
+static cudaError_t launch_snip_fwd_split(const float *value, const int64_t *shapes, const int64_t *lsi,
+                                         const float *offsets, const float *logits, const float *ref, float *out,
+                                         const SnippetDims &d, cudaStream_t stream)
+{
+    const SnipArgs a = make_snip_args<float>(d);
+    const int LP = d.L * d.P;
+    const dim3 grid(d.M, d.Lq, d.N * d.T1);
+    const size_t smem = sizeof(float4) * (LP + 1 + LP * LANES) + sizeof(float) * LP;
+    const bool masked = d.mask != nullptr;
+#define MSDA_LAUNCH_SPLIT(BLOCK_)                                                                                         \
+    do {                                                                                                                  \
+        if (masked)                                                                                                       \
+            msda_snippet_fwd_split_kernel<LANES, BLOCK_, kDirectMasked><<<grid, BLOCK_, smem, stream>>>(                  \
+                value, shapes, lsi, offsets, logits, ref, out, a);                                                        \
+        else                                                                                                              \
+            msda_snippet_fwd_split_kernel<LANES, BLOCK_, kDirect><<<grid, BLOCK_, smem, stream>>>(                        \
+                value, shapes, lsi, offsets, logits, ref, out, a);                                                        \
+    } while (0)
+    if (LP * LANES <= 160) MSDA_LAUNCH_SPLIT(160);
+    else MSDA_LAUNCH_SPLIT(kSnippetMaxLP * LANES);
+#undef MSDA_LAUNCH_SPLIT
+    return cudaGetLastError();
+}
+
 // SCATTER == false (presummed only): grad_offsets / grad_logits alone, no atomics anywhere -- the deterministic
 // mode computes grad_value with the two-pass gather of msda_deterministic.cu.
 template <typename VT, int LANES, int PAIRS, int CSB, int MODE, bool SCATTER = true>
@@ -582,6 +680,10 @@ cudaError_t launch_snippet_forward_f32(const float *value, const int64_t *shapes
                                        const float *logits, const float *ref, float *out,
                                        const SnippetDims &d, cudaStream_t stream)
 {
+    // few queries (decoder): latency-bound -- one CTA per (query, head), samples spread over the threads
+    if (!d.presummed && d.D == 48 && d.Lq <= 65535 && fwd_split_on() &&
+        pick_pairs_d48(snip_pairs_d48(), d.Lq, d.M, d.N * d.T1) == 8)
+        return launch_snip_fwd_split<12>(value, shapes, lsi, offsets, logits, ref, out, d, stream);
 #define CALL(VT, LN, PR) launch_snip_fwd<VT, LN, PR>(value, shapes, lsi, offsets, logits, ref, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL

@@ -1,29 +1,20 @@
-R=gpurun_out/r2j
+R=gpurun_out/r2m
 mkdir -p $R
-timeout 300 python tools/debug/planar_probe.py multi_level_fwd multi_level_bwd encoder_fwd encoder_bwd > $R/probe.log 2>&1; cat $R/probe.log
-ob() { # tag, extra env...
-  tag=$1; shift
-  for regime in init local; do
-    env "$@" timeout 120 python tools/opbench.py --iters 30 --regime $regime --cases snip_enc_N1 --only fwd_planar,bwd_planar | sed "s/\"pairs\": 16/\"variant\": \"$tag\"/" >> $R/opbench_variants.jsonl 2>> $R/opbench.err
-  done
-}
-ob tile2d_p32 A=1
-ob rows_p32 MSDA_PLANAR_TILE2D=0
-ob tile2d_p16 MSDA_PLANAR_PAIRS=16
-ob tile2d_p64 MSDA_PLANAR_PAIRS=64
-tools/debug/variant.sh -DMSDA_PLANAR_FWD_MIN_BLOCKS=5 -DMSDA_PLANAR_BWD_MIN_BLOCKS=5
-ob tile2d_p32_blocks5 A=1
-ob tile2d_p16_blocks5 MSDA_PLANAR_PAIRS=16
-tools/debug/variant.sh -DMSDA_PLANAR_FWD_MIN_BLOCKS=6 -DMSDA_PLANAR_BWD_MIN_BLOCKS=6
-ob tile2d_p32_blocks6 A=1
-ob tile2d_p16_blocks6 MSDA_PLANAR_PAIRS=16
-tools/debug/variant.sh -DMSDA_PLANAR_FWD_MIN_BLOCKS=8 -DMSDA_PLANAR_BWD_MIN_BLOCKS=4
-ob tile2d_p32_blocks8 A=1
-tail -5 $R/opbench.err
+timeout 1200 python -m pytest tests -m gpu -q --maxfail=40 -p timeout --timeout=180 > $R/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $R/pytest_gpu.log; tail -6 $R/pytest_gpu.log
+for regime in init local; do
+  timeout 120 python tools/opbench.py --iters 30 --regime $regime --cases snip_dec_N1 --only fwd_direct | sed "s/\"pairs\": 16/\"variant\": \"split\"/" >> $R/opbench_dec.jsonl 2>> $R/opbench.err
+  MSDA_FWD_SPLIT=0 timeout 120 python tools/opbench.py --iters 30 --regime $regime --cases snip_dec_N1 --only fwd_direct | sed "s/\"pairs\": 16/\"variant\": \"tiles\"/" >> $R/opbench_dec.jsonl 2>> $R/opbench.err
+done
+tail -3 $R/opbench.err
 python - $R <<'PY'
 import json, sys
-for l in open(sys.argv[1] + '/opbench_variants.jsonl'):
+for l in open(sys.argv[1] + '/opbench_dec.jsonl'):
     d = json.loads(l)
-    if d['pass'] in ('fwd_planar', 'bwd_planar'):
-        print("%-6s %-12s %9.2f us %7.1f GB/s %.4f %s" % (d['regime'], d['pass'], d['us_median'], d['GBps'], d['frac_of_measured_hbm'], d.get('variant', '')))
+    print("%-6s %-40s %9.2f us %7.1f GB/s %.4f %s" % (d['regime'], d['pass'], d['us_median'], d['GBps'], d['frac_of_measured_hbm'], d.get('variant', '')))
+PY
+timeout 600 python bench.py --steps 20 --warmup 5 --no-train --no-gpu-baseline --no-cpu-baseline > $R/bench_n1.json 2> $R/bench_n1.err; cut -c1-300 $R/bench_n1.json; tail -2 $R/bench_n1.err
+python - $R <<'PY'
+import json, sys
+d = json.load(open(sys.argv[1] + '/bench_n1.json'))
+for k in d['roofline']['kernels']: print(k)
 PY
