@@ -115,6 +115,57 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
     if (live) acc.store(reinterpret_cast<char *>(out) + (pair * LANES + chunk) * C::BYTES);
 }
 
+// Few-queries forward (decoder-sized Lq): with 8 or 16 queries per CTA such a launch is a handful of CTAs whose
+// lanes walk the L*P samples one after the other -- a chain of dependent round trips to L2 / HBM that the reference's
+// thread-per-output-element kernel does not have (cold L2: 24.6 us against its 19.5 us,
+// profiles/r02_run9_opbench_l2_flushed.jsonl).  Here ONE (query, head) pair owns a CTA and thread = (sample, 16-byte
+// chunk): the location / weight loads are one round trip, the four corner loads a second, and the L*P partial sums
+// meet in shared memory (summed in a fixed order).
+template <int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+msda_fwd_split_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+                      const float *__restrict__ loc, const float *__restrict__ attn, float *__restrict__ out,
+                      const FastArgs a)
+{
+    using C = Chunk<float>;
+    __shared__ LevelTable lv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *red = reinterpret_cast<float4 *>(smem_raw);   // [sample][chunk]
+    const int tid = threadIdx.x;
+    const int m = blockIdx.x, q = blockIdx.y, nb = blockIdx.z;
+    const int LP = a.L * a.P;
+    const int sidx = tid / LANES, lane = tid - sidx * LANES;
+    const size_t pair = ((size_t)nb * a.Lq + q) * a.M + m;
+    // issued before the level table is staged: the sample's own loads do not depend on it
+    float2 uv = make_float2(0.f, 0.f);
+    float at = 0.f;
+    if (sidx < LP) {
+        uv = __ldg(reinterpret_cast<const float2 *>(loc) + pair * LP + sidx);
+        at = __ldg(attn + pair * LP + sidx);
+    }
+    load_level_table(lv, shapes, lsi, a.L, a.S);
+    __syncthreads();
+    if (sidx < LP) {
+        const int l = fast_div(sidx, a.magic_P);
+        const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
+        const float4 r = make_record(s, at, a.cell_bytes);
+        const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
+                         (size_t)(m * LANES + lane) * C::BYTES;
+        C acc = zero_chunk<C>();
+        gather_fma<float, 0>(acc, record_meta(r, (unsigned)(lv.W[l] * a.cell_bytes)), record_weights(r), p0, a.cell_bytes);
+        red[sidx * LANES + lane] = make_float4(acc.x[0], acc.x[1], acc.x[2], acc.x[3]);
+    }
+    __syncthreads();
+    if (tid < LANES) {
+        float4 sum = red[tid];
+        for (int j = 1; j < LP; ++j) {
+            const float4 v = red[j * LANES + tid];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(reinterpret_cast<char *>(out) + (pair * LANES + tid) * C::BYTES) = sum;
+    }
+}
+
 // SCATTER == false: grad_sampling_loc / grad_attn_weight only (deterministic mode computes
 // grad_value separately, msda_deterministic.cu).  grad_value is fp32 for every VT.
 template <typename VT, int LANES, int PAIRS, int CSB, bool SCATTER>
@@ -340,6 +391,26 @@ cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, c
                                     const OpDims &d, cudaStream_t stream)
 {
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
+    // few queries (decoder-sized launches): one CTA per (query, head), samples spread over the threads
+    // (MSDA_FWD_SPLIT=0 in the environment keeps the tile kernel: benchmark knob, read once)
+    static const bool split_on = [] { const char *e = getenv("MSDA_FWD_SPLIT"); return !(e && e[0] == '0'); }();
+    if (split_on && d.D == 48 && d.L * d.P <= 32 && d.Lq <= 65535 && d.N <= 65535 &&
+        (long long)((d.Lq + 15) / 16) * d.M * d.N < 148 * 3) {
+        FastArgs a;
+        a.M = d.M; a.L = d.L; a.P = d.P; a.Lq = d.Lq; a.S = d.S;
+        a.cell_bytes = d.M * d.D * 4;
+        a.cl = d.L * d.P;
+        a.magic_cl = fast_magic(a.cl);
+        a.magic_P = fast_magic(d.P);
+        a.value_batch_stride = d.value_batch_stride;
+        const dim3 grid(d.M, d.Lq, d.N);
+        const size_t smem = sizeof(float4) * d.L * d.P * 12;
+        if (d.L * d.P * 12 <= 160)
+            msda_fwd_split_kernel<12, 160><<<grid, 160, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+        else
+            msda_fwd_split_kernel<12, 384><<<grid, 384, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+        return cudaGetLastError();
+    }
 #define CALL(VT, LN, PR) launch_fwd_fast<VT, LN, PR>(value, shapes, lsi, loc, attn, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
