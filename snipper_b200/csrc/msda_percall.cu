@@ -134,31 +134,39 @@ msda_fwd_split_kernel(const float *__restrict__ value, const int64_t *__restrict
     const int tid = threadIdx.x;
     const int m = blockIdx.x, q = blockIdx.y, nb = blockIdx.z;
     const int LP = a.L * a.P;
+    constexpr int SLOTS = BLOCK / LANES;          // samples in flight per pass; thread = (slot, chunk)
     const int sidx = tid / LANES, lane = tid - sidx * LANES;
     const size_t pair = ((size_t)nb * a.Lq + q) * a.M + m;
-    // issued before the level table is staged: the sample's own loads do not depend on it
+    // issued before the level table is staged: the first sample's own loads do not depend on it
     float2 uv = make_float2(0.f, 0.f);
     float at = 0.f;
-    if (sidx < LP) {
+    if (sidx < LP && sidx < SLOTS) {
         uv = __ldg(reinterpret_cast<const float2 *>(loc) + pair * LP + sidx);
         at = __ldg(attn + pair * LP + sidx);
     }
     load_level_table(lv, shapes, lsi, a.L, a.S);
     __syncthreads();
-    if (sidx < LP) {
-        const int l = fast_div(sidx, a.magic_P);
-        const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
-        const float4 r = make_record(s, at, a.cell_bytes);
+    if (sidx < SLOTS) {
         const char *p0 = reinterpret_cast<const char *>(value + (int64_t)nb * a.value_batch_stride) +
                          (size_t)(m * LANES + lane) * C::BYTES;
         C acc = zero_chunk<C>();
-        gather_fma<float, 0>(acc, record_meta(r, (unsigned)(lv.W[l] * a.cell_bytes)), record_weights(r), p0, a.cell_bytes);
+        for (int sp = sidx; sp < LP; sp += SLOTS) {   // more than SLOTS samples (frames presented as levels): a few passes
+            if (sp != sidx) {
+                uv = __ldg(reinterpret_cast<const float2 *>(loc) + pair * LP + sp);
+                at = __ldg(attn + pair * LP + sp);
+            }
+            const int l = fast_div(sp, a.magic_P);
+            const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
+            const float4 r = make_record(s, at, a.cell_bytes);
+            gather_fma<float, 0>(acc, record_meta(r, (unsigned)(lv.W[l] * a.cell_bytes)), record_weights(r), p0, a.cell_bytes);
+        }
         red[sidx * LANES + lane] = make_float4(acc.x[0], acc.x[1], acc.x[2], acc.x[3]);
     }
     __syncthreads();
     if (tid < LANES) {
         float4 sum = red[tid];
-        for (int j = 1; j < LP; ++j) {
+        const int used = LP < SLOTS ? LP : SLOTS;
+        for (int j = 1; j < used; ++j) {
             const float4 v = red[j * LANES + tid];
             sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
@@ -394,7 +402,7 @@ cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, c
     // few queries (decoder-sized launches): one CTA per (query, head), samples spread over the threads
     // (MSDA_FWD_SPLIT=0 in the environment keeps the tile kernel: benchmark knob, read once)
     static const bool split_on = [] { const char *e = getenv("MSDA_FWD_SPLIT"); return !(e && e[0] == '0'); }();
-    if (split_on && d.D == 48 && d.L * d.P <= 32 && d.Lq <= 65535 && d.N <= 65535 &&
+    if (split_on && d.D == 48 && d.L * d.P <= (1 << 20) && d.Lq <= 65535 && d.N <= 65535 &&
         (long long)((d.Lq + 15) / 16) * d.M * d.N < 148 * 3) {
         FastArgs a;
         a.M = d.M; a.L = d.L; a.P = d.P; a.Lq = d.Lq; a.S = d.S;
@@ -404,7 +412,7 @@ cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, c
         a.magic_P = fast_magic(d.P);
         a.value_batch_stride = d.value_batch_stride;
         const dim3 grid(d.M, d.Lq, d.N);
-        const size_t smem = sizeof(float4) * d.L * d.P * 12;
+        const size_t smem = sizeof(float4) * 32 * 12;   // one partial sum per (sample slot, chunk)
         if (d.L * d.P * 12 <= 160)
             msda_fwd_split_kernel<12, 160><<<grid, 160, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
         else

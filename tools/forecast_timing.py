@@ -20,6 +20,7 @@ def main():
     out = {}
     for fut in (0, 2):
         model = build_snipper(snipper_b200.MSDeformAttn, num_future_frames=fut).to(dev).eval()
+        snipper_b200.enable_fused_layer_tails(model)     # as bench.py runs the network
         x = torch.rand(1, 12, 600, 800, device=dev)
         with torch.no_grad():
             for _ in range(3):
