@@ -1,9 +1,5 @@
-R=gpurun_out/r2q
+R=gpurun_out/r2r
 mkdir -p $R
-timeout 600 python -m pytest tests/test_msda_gpu.py tests/test_fuzz_gpu.py tests/test_capi_c_gpu.py -m gpu -q --maxfail=40 -p timeout --timeout=180 > $R/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $R/pytest_gpu.log; tail -4 $R/pytest_gpu.log
-timeout 300 python tools/opsweep.py --iters 20 --ref --only dec_N1_k4_P8,dec_N1,q300_N1,dec_N64 > $R/opsweep_dec.jsonl 2> $R/opsweep.err; tail -2 $R/opsweep.err
-python - $R <<'PY'
-import json, sys
-for l in open(sys.argv[1] + '/opsweep_dec.jsonl'):
-    d = json.loads(l); print(d['config'], d['impl'], d['pass'], d['us'])
-PY
+timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_fuzz_gpu.py tests/test_msda_gpu.py tests/test_fullsize_gpu.py -m gpu -q -k "planar or packed or levels_points or decoder or ragged or config3" -p timeout --timeout=800 > $R/sanitizer_racecheck.log 2>&1; tail -5 $R/sanitizer_racecheck.log
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_fuzz_gpu.py tests/test_msda_gpu.py tests/test_layers_gpu.py tests/test_module_gpu.py -m gpu -q -p timeout --timeout=800 > $R/sanitizer_memcheck.log 2>&1; tail -5 $R/sanitizer_memcheck.log
+timeout 600 compute-sanitizer --tool synccheck python -m pytest tests/test_fuzz_gpu.py -m gpu -q -k "planar or packed" -p timeout --timeout=500 > $R/sanitizer_synccheck.log 2>&1; tail -4 $R/sanitizer_synccheck.log
