@@ -1,12 +1,12 @@
-// Planar neighbour-frame slots: the encoder's gather / scatter at one L1 wavefront per 128 bytes (sm_100a, fp32, D = 48).
+// Planar neighbour-frame slots (opt-in, MSDA_FLAG_PLANAR): the encoder's gather / scatter with every L1 wavefront a full
+// 128-byte line (sm_100a, fp32, D = 48).
 //
-// What bounds the fused encoder kernels is the L1 data pipe, and its currency is the WAVEFRONT: one per quarter warp
-// (8 lanes x 16 B) and per 128-byte line touched (profiles/r01_run18_*, r01_run48_*).  In the reference layout
-// (.., S, M, D) a head's 48 fp32 channels are a 192-byte slice at a 64-byte-aligned offset of a 1536-byte cell: every
-// corner costs two wavefronts that carry 192 of 256 bytes, and 12 lanes per query leave the quarter warps straddling
-// queries (measured 2.1 wavefronts per corner, 8.4 per sample).  The gather cannot choose the layout of `value` --
-// but the pre-summed slots (msda_frames.cu: sum over neighbour frames, taken before the gather by linearity) are a
-// buffer of OUR OWN, written once per layer by a streaming pass.  So that pass writes them PLANAR, per (n, slot):
+// In the reference layout (.., S, M, D) a head's 48 fp32 channels are a 192-byte slice at a 64-byte-aligned offset of a
+// 1536-byte cell: every corner costs two L1 wavefronts that carry 192 of 256 bytes, and 12 lanes per query leave the
+// quarter warps straddling queries (measured 2.1 wavefronts per corner, 8.4 per sample).  The gather cannot choose the
+// layout of `value` -- but the pre-summed slots (msda_frames.cu: sum over neighbour frames, taken before the gather by
+// linearity) are a buffer of OUR OWN, written once per layer by a streaming pass.  So that pass can write them PLANAR,
+// per (n, slot):
 //
 //   plane A   [m][s]    channels  0..31 of head m at pixel s: one 128-byte line per cell
 //   plane Be  [m][s]    channels 32..47, 64-byte cells: x-adjacent cells (s, s+1) share a line when s is even
@@ -14,17 +14,22 @@
 //
 // and a query is served by ONE QUARTER WARP (8 lanes): per sample 4 x LDG.128 on plane A (one line each) and
 // 2 x LDG.128 on plane B (lanes 0-3 the (y,x0) cell, lanes 4-7 the (y,x0+1) cell of row y0 / y0+1, from whichever copy
-// has the pair line-aligned) -- 6 wavefronts per sample, every one a full line, against 8.4; the sample record is one
-// broadcast LDS.128 per quarter warp (1 wavefront per query and sample instead of 1.5).  The backward scatters the same
-// way (6 full-line vector reductions per sample) into planar fp32 slots that msda_frame_unsum_planar folds back into
+// has the pair line-aligned) -- 6 wavefronts per sample, every one a full line.  The backward scatters the same way
+// (6 full-line vector reductions per sample) into planar fp32 slots that msda_frame_unsum_planar folds back into
 // grad_value (N,T2,S,M,D).  Cost: the slots take 4/3 of the bytes (Be and Bo hold the same 16 channels).
+//
+// MEASURED (profiles/r02_run6_* .. r02_run8_*): 20 % fewer global-load wavefronts and, with the
+// quarter-warp-local set-up below, 30 % fewer instructions than the cell-major kernels -- at the SAME speed (166 vs
+// 164 us per encoder layer): both layouts run at the rate of the L1 global-load path, which does not depend on line
+// utilisation.  Hence opt-in, not the default.  The layout is kept because a window of a planar slot is a set of
+// contiguous row segments, which is what a shared-memory staged gather needs.
 //
 // Pad cells (Bo cell 0 of each head, the tail of each B plane) are never read with a live lane and never written by
 // the scatter: a pair is only loaded / reduced as a whole when all four corners of the sample are inside the level
 // (then s and s+1 are pixels of one row); border samples take the per-corner predicated path.
 //
-// Math and operation order are those of msda_snippet.cu (phase 1 is shared: msda_snippet_common.cuh); only the
-// summation order over channels / corners inside one output element differs, as it does between any two lane mappings.
+// Math and operation order per sample are those of msda_snippet.cu; the softmax denominator and the sums over
+// channels / corners inside one output element are taken in a different order, as between any two lane mappings.
 #include "msda_snippet_common.cuh"
 
 namespace msda {
