@@ -98,6 +98,25 @@ def test_fused_and_mask_entry_points_validate_without_a_gpu():
     assert fsum(N=0, n_frame=5) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert fsum(N=0, dtype=F64) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
     assert fsum(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT
+    # planar slots (opt-in): the layout exists for float32 heads of 48 channels; it rides on the pre-summed path only
+    PLN = capi.MSDA_FLAG_PLANAR
+    assert L.msda_planar_slot_bytes(9875, 8, 48, F32) == 8 * (9875 * 128 + 9878 * 128)   # plane A + two copies of plane B
+    assert L.msda_planar_slot_bytes(9875, 8, 32, F32) == 0 and L.msda_planar_slot_bytes(9875, 8, 48, BF16) == 0
+    assert L.msda_planar_slot_bytes(0, 8, 48, F32) == 0 and L.msda_planar_slot_bytes(1 << 22, 8, 48, F32) == 0   # 32-bit offsets
+    assert fwd(N=0, flags=PRE | PLN) == capi.MSDA_OK
+    assert fwd(N=0, flags=PLN) == capi.MSDA_ERR_INVALID_ARGUMENT              # planar without pre-summed slots
+    assert fwd(N=0, flags=PRE | PLN, dtype=BF16) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert fwd(N=0, flags=PRE | PLN, D=32) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert fwd(flags=PRE | PLN, ptr=320) == capi.MSDA_ERR_INVALID_ARGUMENT     # slots must be 128-byte aligned
+    assert bwd(PRE | PLN | DET) == capi.MSDA_ERR_INVALID_ARGUMENT              # the deterministic mode walks cell-major slots
+    def fsum_pl(N=1, T2=4, T1=4, n_frame=4, S=100, M=8, D=48, dtype=F32, ptr=256, mask=None, mrs=0, mcs=0):
+        return L.msda_frame_sum_planar(ptr, mask, ptr, N, T2, T1, n_frame, S, M, D, 0, 0, mrs, mcs, dtype, 0)
+    assert fsum_pl(N=0) == capi.MSDA_OK
+    assert fsum_pl(N=0, D=64) == capi.MSDA_ERR_UNSUPPORTED_DTYPE and fsum_pl(N=0, dtype=BF16) == capi.MSDA_ERR_UNSUPPORTED_DTYPE
+    assert fsum_pl(N=0, n_frame=5) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert fsum_pl(ptr=0) == capi.MSDA_ERR_INVALID_ARGUMENT and fsum_pl(ptr=336) == capi.MSDA_ERR_INVALID_ARGUMENT
+    assert L.msda_frame_unsum_planar(256, None, 256, 0, 4, 4, 4, 100, 8, 48, 0, 0, F32, 0) == capi.MSDA_OK
+    assert L.msda_frame_unsum_planar(336, None, 256, 1, 4, 4, 4, 100, 8, 48, 0, 0, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
     assert L.msda_frame_unsum(0, None, 0, 0, 4, 4, 4, 100, 384, 0, 0, F32, 0) == capi.MSDA_OK
     assert L.msda_frame_unsum(0, None, 0, 1, 4, 4, 4, 100, 384, 0, 0, F32, 0) == capi.MSDA_ERR_INVALID_ARGUMENT
     # layer tail: float32 rows of 128*k <= 1024 channels; pos and its output come together
