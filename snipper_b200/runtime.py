@@ -11,12 +11,18 @@ construction: no host synchronisation, every shape table read on the device, all
 
 ``out`` is whatever the function returned during capture (tensors / dicts / lists / tuples of them); the
 tensors are the graph's STATIC output buffers -- read or copy them before the next call with the same shape.
+
+Input pipelining: ``runner.prefetch(next_frames)`` starts the host-to-device copy of the NEXT input on a side
+stream into a staging buffer; the following ``runner(next_frames)`` (same tensor object) only does a device-to-device
+copy before the replay, so the PCIe transfer of snippet i+1 overlaps the compute of snippet i:
+
+    out = runner(frames[i]); runner.prefetch(frames[i + 1]); consume(out)
 """
 import torch
 
 
 class _Entry:
-    __slots__ = ("graph", "static_in", "static_out", "launches")
+    __slots__ = ("graph", "static_in", "static_out", "launches", "staging", "staged", "staged_evt", "free_evt")
 
 
 class GraphRunner:
@@ -51,6 +57,7 @@ class GraphRunner:
         with torch.cuda.graph(e.graph):
             e.static_out = self._run(e.static_in)
         e.launches = ops.STATS.launches - before   # kernels of this package inside one replay
+        e.staging, e.staged, e.staged_evt, e.free_evt = None, None, None, None
         return e
 
     def entry(self, x):
@@ -64,9 +71,34 @@ class GraphRunner:
         """Launches of this package's kernels inside one replay for inputs shaped like ``x``."""
         return self.entry(x).launches
 
+    def prefetch(self, x):
+        """Start copying the NEXT input (a pinned host tensor) to the device on a side stream.  The call that follows with
+        the same tensor object picks the staged copy up; any other input is copied directly as usual."""
+        e = self.entry(x)
+        dev = e.static_in.device
+        if e.staging is None:
+            e.staging = torch.empty_like(e.static_in)
+            self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        if e.free_evt is not None:
+            cs.wait_event(e.free_evt)            # the previous staged input has left the staging buffer
+        with torch.cuda.stream(cs):
+            e.staging.copy_(x, non_blocking=True)
+            e.staged_evt = torch.cuda.Event()
+            e.staged_evt.record(cs)
+        e.staged = x
+
     def __call__(self, x):
         """``x``: a CUDA tensor, or a (pinned) host tensor -- copied into the static input asynchronously."""
         e = self.entry(x)
-        e.static_in.copy_(x, non_blocking=True)
+        if e.staged is x and e.staged_evt is not None:
+            main = torch.cuda.current_stream(e.static_in.device)
+            main.wait_event(e.staged_evt)
+            e.static_in.copy_(e.staging, non_blocking=True)
+            e.free_evt = torch.cuda.Event()
+            e.free_evt.record(main)
+            e.staged = None
+        else:
+            e.static_in.copy_(x, non_blocking=True)
         e.graph.replay()
         return e.static_out

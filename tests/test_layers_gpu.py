@@ -118,6 +118,17 @@ def test_graph_runner_replays_bit_identically_and_counts_launches():
     got = runner(host)                                                            # pinned host input: H2D inside the call
     torch.cuda.synchronize()
     assert torch.equal(got["pred_kpts2d"], eager[0]["pred_kpts2d"])
+    # input pipelining: the next snippet's H2D copy is staged on a side stream while the current one computes
+    hosts = [x.cpu().pin_memory() for x in xs]
+    runner.prefetch(hosts[0])
+    for i in range(6):
+        got = runner(hosts[i % 3])                                                # picks the staged copy up
+        runner.prefetch(hosts[(i + 1) % 3])
+        torch.cuda.synchronize()
+        assert torch.equal(got["pred_kpts2d"], eager[i % 3]["pred_kpts2d"]), i
+    got = runner(hosts[2])                                                        # not the staged tensor: direct copy
+    torch.cuda.synchronize()
+    assert torch.equal(got["pred_kpts2d"], eager[2]["pred_kpts2d"])
     other = torch.rand(2, 12, 128, 160, device=DEV)                               # a second resolution gets its own graph
     with torch.no_grad():
         want = fn(other)["pred_logits"].clone()
