@@ -5,7 +5,7 @@
 R=gpurun_out/${1:-check}
 mkdir -p $R
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $R/smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > $R/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $R/pytest_gpu.log; tail -15 $R/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q -p timeout --timeout=180 > $R/pytest_gpu.log 2>&1   # per-test timeout: a hung kernel must not eat the job; echo "pytest exit $?" >> $R/pytest_gpu.log; tail -15 $R/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > $R/smoke.log 2>&1; tail -3 $R/smoke.log
 rm -f $R/opbench.jsonl
 for regime in init local; do
