@@ -579,6 +579,21 @@ def main():
     }
     if train is not None:
         line["train"] = train
+        # the backward's own roofline entry (BASELINE metric: "MSDeformAttn fwd/bwd HBM GB/s"): the fused encoder
+        # backward as timed inside the training step (batch 2), same accounting as `roofline`
+        bwd = next((k for k in train.get("msda_kernels", []) if k["kernel"].startswith("snippet_backward") and
+                    k["algorithmic_MB"] and "x9875x4" in k["dims"] and k["dims"].split("x")[7] == "9875"), None)
+        if bwd is not None:
+            btraffic, bsrc = recorded_traffic("snippet_backward_presummed_encoder_dram_bytes_per_launch")
+            n_batch = int(bwd["dims"].split("x")[0])
+            line["roofline_backward"] = {
+                "bound": "hbm", "kernel": "msda_snippet_bwd_kernel<float,12,16,1536,presummed> (%s %s)" % (bwd["kernel"], bwd["dims"]),
+                "achieved": bwd["GBps"], "peak": peak, "unit": "GB/s", "frac": bwd["GBps"] / peak,
+                "traffic": None if btraffic is None else btraffic * n_batch,
+                "traffic_source": "%s, captured at batch 1 and scaled by the batch" % bsrc,
+                "algorithmic_bytes_per_launch": int(bwd["algorithmic_MB"] * 1e6), "avg_launch_ms": bwd["avg_us"] / 1e3,
+                "how": "CUDA events around each launch in two training steps after the timed region",
+                "limiter": "SM->L2 request path (vector reductions), see DESIGN.md section 3"}
     if world == 1 and not args.no_gpu_baseline:
         line["gpu_baseline"] = gpu_baseline_run(dev)
     if world == 1 and not args.no_cpu_baseline:
