@@ -218,7 +218,7 @@ def source_fingerprint():
     return h.hexdigest()[:16]
 
 
-EXTRA_WARMUP = 40   # untimed replays before the timed regions, in addition to --warmup (see main)
+EXTRA_WARMUP = 120   # untimed replays before the timed regions, in addition to --warmup (see main)
 
 
 def recorded_traffic(key):
@@ -494,9 +494,11 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    # steady state: the first ~40 replays of a fresh process run ~2 % slower whatever the issue pattern
-    # (profiles/r02_run22_replay_modes_probe.json), so the resident loop gets extra untimed replays on top of --warmup
-    for i in range(EXTRA_WARMUP):
+    # steady state: on a fresh box the first seconds of replays run ~2 % slower whatever the issue pattern
+    # (profiles/r02_run22_replay_modes_probe.json, r02_run23_*), so the resident loop gets extra untimed replays on top
+    # of --warmup: a fixed 120 (about 3 s), after which consecutive blocks of replays agree
+    extra_warmup = EXTRA_WARMUP
+    for i in range(extra_warmup):
         step_resident(i)
     ops.STATS.reset()
     ms_total = timed(step_resident, args.steps, args.warmup)
@@ -568,7 +570,7 @@ def main():
                    "precision_note": "fp32 = torch defaults: fp32 SIMT GEMMs for the Linear layers, cuDNN convolutions may use TF32 "
                                      "(torch.backends.cudnn.allow_tf32 default); the CPU arm is strict fp32",
                    "fused_layer_tails": "%d layers (snipper_b200.enable_fused_layer_tails)" % fused_tails,
-                   "extra_untimed_warmup_steps": EXTRA_WARMUP,
+                   "extra_untimed_warmup_steps": extra_warmup,
                    "msda_ms_per_step_eager_events": msda_ms_per_step},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps},

@@ -1,3 +1,8 @@
-R=gpurun_out/r2x
+R=gpurun_out/r2z
 mkdir -p $R
-timeout 300 python tools/debug/replay_modes.py > $R/replay_modes.json 2> $R/replay_modes.err; cat $R/replay_modes.json; tail -2 $R/replay_modes.err
+for i in 1 2; do timeout 900 python bench.py --steps 20 --warmup 5 2>> $R/bench.err | grep '^{' >> $R/bench_n1_x2.jsonl; done
+python - $R <<'PY'
+import json, sys
+for l in open(sys.argv[1] + '/bench_n1_x2.jsonl'):
+    d = json.loads(l); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['extra_untimed_warmup_steps'], d['train']['value'], d['gpu_baseline']['value'])
+PY
