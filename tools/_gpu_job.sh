@@ -1,8 +1,10 @@
-R=gpurun_out/r2z
+R=gpurun_out/r2final
 mkdir -p $R
-for i in 1 2; do timeout 900 python bench.py --steps 20 --warmup 5 2>> $R/bench.err | grep '^{' >> $R/bench_n1_x2.jsonl; done
-python - $R <<'PY'
+timeout 1500 python -m pytest tests -m gpu -x -q -p timeout --timeout=180 > $R/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $R/pytest_gpu.log; tail -3 $R/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $R/smoke.log 2>&1; tail -2 $R/smoke.log
+timeout 600 python bench.py > $R/bench_default.json 2> $R/bench_default.err; python - $R <<'PY'
 import json, sys
-for l in open(sys.argv[1] + '/bench_n1_x2.jsonl'):
-    d = json.loads(l); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['extra_untimed_warmup_steps'], d['train']['value'], d['gpu_baseline']['value'])
+d = json.load(open(sys.argv[1] + '/bench_default.json'))
+print({k: d[k] for k in ('metric','value','unit','n_gpus','steps','warmup','ms_per_step','higher_is_better','scaling','vs_baseline','dtype','data','gpu_launches')})
+print(d['e2e'], d['clocks']); print({k: d['roofline'][k] for k in ('bound','achieved','peak','unit','frac','traffic')}); print(d['cpu_baseline'])
 PY
