@@ -1,10 +1,13 @@
-R=gpurun_out/r2final
+R=gpurun_out/r2ab
 mkdir -p $R
-timeout 1500 python -m pytest tests -m gpu -x -q -p timeout --timeout=180 > $R/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $R/pytest_gpu.log; tail -3 $R/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $R/smoke.log 2>&1; tail -2 $R/smoke.log
-timeout 600 python bench.py > $R/bench_default.json 2> $R/bench_default.err; python - $R <<'PY'
+ob() { tag=$1; for regime in init local; do timeout 120 python tools/opbench.py --iters 30 --regime $regime --cases snip_enc_N1,enc_N1 --only presummed | grep -v deterministic | sed "s/\"pairs\": 16/\"variant\": \"$tag\"/" >> $R/opbench.jsonl 2>> $R/opbench.err; done; }
+ob default
+MSDA_NVCC_EXTRA="-DMSDA_LOAD_EVICT_LAST" python -c "from snipper_b200 import build; build.build_library(force=True)" > $R/build.log 2>&1; tail -1 $R/build.log
+ob evict_last
+timeout 300 ncu --set full --clock-control none -k regex:"msda_snippet_bwd_kernel" -s 1 -c 1 -o $R/ncu_bwd_evict_last python tools/opbench.py --iters 1 --warmup 1 --inner 1 --regime init --cases snip_enc_N1 --only bwd_presummed > $R/ncu.log 2>&1
+python - $R <<'PY'
 import json, sys
-d = json.load(open(sys.argv[1] + '/bench_default.json'))
-print({k: d[k] for k in ('metric','value','unit','n_gpus','steps','warmup','ms_per_step','higher_is_better','scaling','vs_baseline','dtype','data','gpu_launches')})
-print(d['e2e'], d['clocks']); print({k: d['roofline'][k] for k in ('bound','achieved','peak','unit','frac','traffic')}); print(d['cpu_baseline'])
+for l in open(sys.argv[1] + '/opbench.jsonl'):
+    d = json.loads(l)
+    print("%-12s %-6s %-40s %9.2f us %s" % (d['case'], d['regime'], d['pass'], d['us_median'], d.get('variant', '')))
 PY
