@@ -147,6 +147,21 @@ def test_decoder_layer_config3_forecasting(dtype, presum, per_pixel_mask, planar
     _compare(got, want, dtype, c["pix"], presum)
 
 
+@pytest.mark.parametrize("per_pixel_mask", [True, False])
+def test_decoder_layer_bench_launch(per_pixel_mask):
+    """The decoder launch bench.py times (BASELINE config 2: T1 = T2 = 4, 60 queries): the few-queries split kernel with
+    the padding mask applied in the gather, forward and every gradient against the oracle."""
+    from snipper_b200 import ops
+    c = _case(1, 4, 4, 60, seed=34, encoder=False, sigma_px=6.0)
+    want = _oracle(c, 4, torch.float32)
+    ops.STATS.reset()
+    ops.STATS.timing = True
+    got = _ours(c, 4, torch.float32, None, per_pixel_mask)          # presum=None: the shapes pick the direct gather
+    ops.STATS.timing = False
+    assert sorted({e[0] for e in ops.STATS.events}) == ["snippet_backward", "snippet_forward"]
+    _compare(got, want, torch.float32, c["pix"])
+
+
 def test_auto_strategy_matches_the_shapes():
     from snipper_b200 import ops
     S = sum(h * w for h, w in LEVELS)
