@@ -121,13 +121,14 @@ msda_fwd_fast_kernel(const typename Chunk<VT>::elem *__restrict__ value, const i
 // profiles/r02_run9_opbench_l2_flushed.jsonl).  Here ONE (query, head) pair owns a CTA and thread = (sample, 16-byte
 // chunk): the location / weight loads are one round trip, the four corner loads a second, and the L*P partial sums
 // meet in shared memory (summed in a fixed order).
-template <int LANES, int BLOCK>
+template <typename VT, int LANES, int BLOCK>   // VT = float (16-byte lanes) or bf16q (8-byte lanes): 4 channels per lane
 __global__ void __launch_bounds__(BLOCK)
-msda_fwd_split_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
-                      const float *__restrict__ loc, const float *__restrict__ attn, float *__restrict__ out,
-                      const FastArgs a)
+msda_fwd_split_kernel(const typename Chunk<VT>::elem *__restrict__ value, const int64_t *__restrict__ shapes,
+                      const int64_t *__restrict__ lsi, const float *__restrict__ loc, const float *__restrict__ attn,
+                      typename Chunk<VT>::elem *__restrict__ out, const FastArgs a)
 {
-    using C = Chunk<float>;
+    using C = Chunk<VT>;
+    static_assert(C::N == 4, "one float4 of partial sums per lane");
     __shared__ LevelTable lv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *red = reinterpret_cast<float4 *>(smem_raw);   // [sample][chunk]
@@ -158,7 +159,7 @@ msda_fwd_split_kernel(const float *__restrict__ value, const int64_t *__restrict
             const int l = fast_div(sp, a.magic_P);
             const Sample<float> s = make_sample<float>(uv.x, uv.y, lv.H[l], lv.W[l], lv.start[l]);
             const float4 r = make_record(s, at, a.cell_bytes);
-            gather_fma<float, 0>(acc, record_meta(r, (unsigned)(lv.W[l] * a.cell_bytes)), record_weights(r), p0, a.cell_bytes);
+            gather_fma<VT, 0>(acc, record_meta(r, (unsigned)(lv.W[l] * a.cell_bytes)), record_weights(r), p0, a.cell_bytes);
         }
         red[sidx * LANES + lane] = make_float4(acc.x[0], acc.x[1], acc.x[2], acc.x[3]);
     }
@@ -170,8 +171,37 @@ msda_fwd_split_kernel(const float *__restrict__ value, const int64_t *__restrict
             const float4 v = red[j * LANES + tid];
             sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
-        *reinterpret_cast<float4 *>(reinterpret_cast<char *>(out) + (pair * LANES + tid) * C::BYTES) = sum;
+        C o;
+        o.x[0] = sum.x; o.x[1] = sum.y; o.x[2] = sum.z; o.x[3] = sum.w;
+        o.store(reinterpret_cast<char *>(out) + (pair * LANES + tid) * C::BYTES);
     }
+}
+
+// few queries (decoder-sized launches): one CTA per (query, head), samples spread over the threads
+// (MSDA_FWD_SPLIT=0 in the environment keeps the tile kernel: benchmark knob, read once)
+template <typename VT>
+static bool launch_fwd_split(const typename Chunk<VT>::elem *value, const int64_t *shapes, const int64_t *lsi,
+                             const float *loc, const float *attn, typename Chunk<VT>::elem *out, const OpDims &d,
+                             cudaStream_t stream)
+{
+    static const bool split_on = [] { const char *e = getenv("MSDA_FWD_SPLIT"); return !(e && e[0] == '0'); }();
+    if (!(split_on && d.D == 48 && d.L * d.P <= (1 << 20) && d.Lq <= 65535 && d.N <= 65535 &&
+          (long long)((d.Lq + 15) / 16) * d.M * d.N < 148 * 3))
+        return false;
+    FastArgs a;
+    a.M = d.M; a.L = d.L; a.P = d.P; a.Lq = d.Lq; a.S = d.S;
+    a.cell_bytes = d.M * d.D * (int)sizeof(typename Chunk<VT>::elem);
+    a.cl = d.L * d.P;
+    a.magic_cl = fast_magic(a.cl);
+    a.magic_P = fast_magic(d.P);
+    a.value_batch_stride = d.value_batch_stride;
+    const dim3 grid(d.M, d.Lq, d.N);
+    const size_t smem = sizeof(float4) * 32 * 12;   // one partial sum per (sample slot, chunk)
+    if (d.L * d.P * 12 <= 160)
+        msda_fwd_split_kernel<VT, 12, 160><<<grid, 160, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+    else
+        msda_fwd_split_kernel<VT, 12, 384><<<grid, 384, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
+    return true;
 }
 
 // SCATTER == false: grad_sampling_loc / grad_attn_weight only (deterministic mode computes
@@ -399,26 +429,7 @@ cudaError_t launch_forward_fast_f32(const float *value, const int64_t *shapes, c
                                     const OpDims &d, cudaStream_t stream)
 {
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
-    // few queries (decoder-sized launches): one CTA per (query, head), samples spread over the threads
-    // (MSDA_FWD_SPLIT=0 in the environment keeps the tile kernel: benchmark knob, read once)
-    static const bool split_on = [] { const char *e = getenv("MSDA_FWD_SPLIT"); return !(e && e[0] == '0'); }();
-    if (split_on && d.D == 48 && d.L * d.P <= (1 << 20) && d.Lq <= 65535 && d.N <= 65535 &&
-        (long long)((d.Lq + 15) / 16) * d.M * d.N < 148 * 3) {
-        FastArgs a;
-        a.M = d.M; a.L = d.L; a.P = d.P; a.Lq = d.Lq; a.S = d.S;
-        a.cell_bytes = d.M * d.D * 4;
-        a.cl = d.L * d.P;
-        a.magic_cl = fast_magic(a.cl);
-        a.magic_P = fast_magic(d.P);
-        a.value_batch_stride = d.value_batch_stride;
-        const dim3 grid(d.M, d.Lq, d.N);
-        const size_t smem = sizeof(float4) * 32 * 12;   // one partial sum per (sample slot, chunk)
-        if (d.L * d.P * 12 <= 160)
-            msda_fwd_split_kernel<12, 160><<<grid, 160, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
-        else
-            msda_fwd_split_kernel<12, 384><<<grid, 384, smem, stream>>>(value, shapes, lsi, loc, attn, out, a);
-        return cudaGetLastError();
-    }
+    if (launch_fwd_split<float>(value, shapes, lsi, loc, attn, out, d, stream)) return cudaGetLastError();
 #define CALL(VT, LN, PR) launch_fwd_fast<VT, LN, PR>(value, shapes, lsi, loc, attn, out, d, stream)
     MSDA_DISPATCH_LANES(d.D, CALL)
 #undef CALL
@@ -443,6 +454,7 @@ cudaError_t launch_forward_fast_bf16(const void *value_, const int64_t *shapes, 
     if (d.N * d.Lq * d.M == 0) return cudaSuccess;
     const __nv_bfloat16 *value = static_cast<const __nv_bfloat16 *>(value_);
     __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(out_);
+    if (launch_fwd_split<bf16q>(value, shapes, lsi, loc, attn, out, d, stream)) return cudaGetLastError();
     // few CTAs (decoder-sized Lq): latency-bound -- 8-byte lanes give twice the threads per query
     // (measured 20-45 % faster there, profiles/r01_run14_*); large grids keep the 16-byte lanes.
     if ((long long)((d.Lq + 15) / 16) * d.M * d.N < 148 * 3) {
