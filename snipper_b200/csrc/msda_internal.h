@@ -9,6 +9,10 @@ namespace msda {
 
 constexpr int kMaxLevels = 64;
 
+// Dynamic shared memory above which a launcher opts in with cudaFuncAttributeMaxDynamicSharedMemorySize: the 48 KB
+// default limit covers STATIC + dynamic shared memory, and every kernel here also holds a static level table (~1 KB).
+constexpr size_t kSmemOptIn = 44 * 1024;
+
 struct OpDims {
     int N, S, M, D, L, Lq, P;
     int64_t value_batch_stride;  // elements

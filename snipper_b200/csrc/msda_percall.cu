@@ -382,7 +382,7 @@ static cudaError_t launch_bwd_fast(const typename Chunk<VT>::elem *value, const 
         msda_bwd_fast_kernel<VT, LANES, PAIRS, C, SCATTER><<<grid, Cfg::THREADS, smem, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, grad_value, grad_loc, grad_attn, a);
     } else {
-        if (smem > 48 * 1024) {  // wide heads x many samples per pass (D = 128, L*P = 32: 57.6 KB)
+        if (smem > kSmemOptIn) {  // wide heads x many samples per pass (D = 128, L*P = 32: 57.6 KB)
             const cudaError_t e = cudaFuncSetAttribute(msda_bwd_fast_kernel<VT, LANES, PAIRS, 0, SCATTER>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
